@@ -1,0 +1,174 @@
+/* ldt_b200 -- C ABI of the B200 (sm_100a) kernels behind the LDT sampling hot path.
+ *
+ * The reference (Negai-98/LDT) has no FFI for its model path: the seams are Python call signatures
+ * (SURVEY.md section 8b).  Its one native seam is the StructuralLosses torch extension.  Every entry
+ * point below names the reference interface it replaces; the Python host mirror in ldt_b200/ binds
+ * them with ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name says host;
+ *   - the caller owns every buffer including workspaces; nothing here allocates device memory,
+ *     synchronises the device, or throws;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); work is enqueued on it;
+ *   - return 0 on success, a negative LDT_ERR_* code otherwise; ldt_last_error_string() describes the
+ *     most recent failure on the calling thread;
+ *   - tensors are dense row-major; "token-major" means [batch * tokens, channels].
+ */
+#ifndef LDT_B200_H_
+#define LDT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDT_ABI_VERSION 1
+
+#define LDT_OK 0
+#define LDT_ERR_INVALID (-1)
+#define LDT_ERR_CUDA (-2)
+#define LDT_ERR_UNSUPPORTED (-3)
+#define LDT_ERR_WORKSPACE (-4)
+
+int ldt_abi_version(void);
+const char* ldt_last_error_string(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Metrics
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Nearest-neighbour squared distances, both directions, with argmin indices.
+ * Replaces nndistance() -- evaluation/pytorch_structural_losses/src/nndistance.cu:125-128, bound as
+ * StructuralLossesBackend.NNDistance (src/structural_loss.cpp:80-99, pybind/bind.cpp:14).
+ *   xyz1 [b,n,3] f32, xyz2 [b,m,3] f32 -> dist1 [b,n] f32, idx1 [b,n] i32, dist2 [b,m], idx2 [b,m].
+ * Distances and indices are bit-identical to the reference kernel (lowest index wins ties). */
+int ldt_nn_distance(int b, int n, const float* xyz1, int m, const float* xyz2, float* dist1, int* idx1,
+                    float* dist2, int* idx2, void* stream);
+
+/* Rows [row_begin,row_end) of the pairwise Chamfer matrix
+ *   M[i,j] = mean_p min_q |a_i[p]-b_j[q]|^2 + mean_q min_p |a_i[p]-b_j[q]|^2
+ * Replaces the Python double loop _pairwise_CD_ (evaluation/evaluation_metrics.py:165-198), i.e.
+ * 2*na*ceil(nb/batch) launches of NmDistanceKernel plus expand/mean/cat, by one launch.
+ *   a [na,pa,3] f32, b [nb,pb,3] f32 -> out [(row_end-row_begin), nb] f32 (row-major). */
+int ldt_pairwise_cd(int na, int nb, int pa, int pb, const float* a, const float* b, int row_begin, int row_end,
+                    float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense contraction core (used by the score net and the decoder; exported for parity tests)
+ *   C[M,N] = epilogue( A[M,K] . W[N,K]^T + bias[N] )
+ * A, W are bf16 K-major (row-major with K contiguous, leading dimensions lda/ldw in elements,
+ * multiples of 8; K a multiple of 64).  W is exactly a Conv1d(k=1)/Linear weight [out,in].
+ * This is what replaces every nn.Conv1d(k=1)/nn.Linear on the path (model/layers.py:159-161,
+ * 120-124, 172, 238; model/scorenet/score.py:95; model/Compressor/Network.py:61,153).
+ * ------------------------------------------------------------------------------------------------ */
+enum ldt_epilogue {
+  LDT_EPI_BIAS_F32 = 0,       /* out f32  = acc + bias                                            */
+  LDT_EPI_BIAS_BF16 = 1,      /* out bf16 = acc + bias                                            */
+  LDT_EPI_BIAS_GELU_BF16 = 2, /* out bf16 = gelu_erf(acc + bias)       (MLP fc, layers.py:127-128) */
+  LDT_EPI_GATE_RESID_F32 = 3, /* out f32  = resid + gate[row/rows_per_gate] * (acc + bias); gate may
+                                 be NULL (= 1): x + gate*f(x) of layers.py:218-219,225-226           */
+};
+
+typedef struct ldt_gemm_args {
+  int M, N, K;
+  const void* A;   /* bf16 [M, lda]   */
+  int lda;
+  const void* W;   /* bf16 [N, ldw]   */
+  int ldw;
+  const float* bias; /* [N] or NULL   */
+  void* out;       /* f32 or bf16 [M, ldo] */
+  int ldo;
+  int epilogue;    /* enum ldt_epilogue */
+  const float* resid; /* f32 [M, ldo] (may alias out) for LDT_EPI_GATE_RESID_F32 */
+  const float* gate;  /* f32 rows of length >= N; row r of the output uses gate + (r / rows_per_gate) *
+                         gate_stride; gate_stride == 0 broadcasts one row */
+  long long gate_stride;
+  int rows_per_gate;
+  int backend;     /* 0 = tcgen05/TMEM/TMA kernel (product path); 1 = mma.sync cross-check kernel */
+} ldt_gemm_args;
+
+int ldt_gemm_bf16(const ldt_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Element-wise / normalisation kernels of the score net and decoder
+ * ------------------------------------------------------------------------------------------------ */
+
+/* f32 [rows, cols] -> bf16 [rows, ld_out] with zero padding of columns cols..ld_out-1. */
+int ldt_cast_pad_bf16(int rows, int cols, const float* in, int ld_in, void* out, int ld_out, void* stream);
+
+/* Weight packing: f32 [rows, cols] -> bf16 [rows, ld_out] (zero padded), same kernel, named for the
+ * pack step SURVEY.md 8b lists (ldt_pack_weights). */
+int ldt_pack_weights(int rows, int cols, const float* w, int ld_in, void* out, int ld_out, void* stream);
+
+/* LayerNorm over channels (eps 1e-6, tools/utils.py:127-133) fused with either AdaLN modulation
+ *   y = LN(x) * (1 + scale[g]) + shift[g]     (model/layers.py:136-137, 218-219; g = row / rows_per_mod)
+ * or an element-wise affine (weight, bias) (decoder blocks, layers.py:163-164 with dim_c None);
+ * pass shift/scale or weight/bias, the other pair NULL.  x f32 [rows, C] -> y bf16 [rows, C]. */
+int ldt_layernorm_mod_bf16(int rows, int C, const float* x, const float* shift, const float* scale,
+                           long long mod_stride, int rows_per_mod, const float* weight, const float* bias,
+                           float eps, void* y, void* stream);
+
+/* Sinusoidal time features -> Linear -> SiLU -> Linear (+ optional additive embedding) -> SiLU.
+ * Replaces TimeEmbedding.forward (model/layers.py:14-41) and the leading SiLU of every adaLN
+ * (layers.py:172,237).  t [R] f32, freq [half] f32 (host-computed exactly as layers.py:28-30),
+ * w0 [D, 2*half], w1 [D, D] f32 -> c [R, D] f32 (pre-SiLU, what Score.forward calls `c`) and
+ * silu_c bf16 [R_pad, D] (the A operand of the adaLN GEMMs).  extra [R, D] f32 or NULL is added to c
+ * (label / image-condition embedding, score.py:135). */
+int ldt_time_embedding(int R, int half, int D, const float* t, const float* freq, const float* w0,
+                       const float* b0, const float* w1, const float* b1, const float* extra, float* c,
+                       void* silu_c, float* scratch /* [R, D + 2*half] f32 */, void* stream);
+
+/* Multi-head attention over a short key set, one (batch, head) pair per warp group.
+ *   q  bf16 [B*Nq, ldq]  (head h uses columns h*dh..h*dh+dh-1 -- contiguous channel groups,
+ *                          layers.py:192-194)
+ *   k,v bf16 [B*Nk, ldkv] likewise
+ *   o  bf16: written as the reference's (w@v).reshape(B,N,C) does (layers.py:197): the [B,H,Nq,dh]
+ *      result buffer is stored contiguously and re-read as token-major [B*Nq, H*dh] WITHOUT permuting
+ *      heads back.  This quirk is part of the trained weights' meaning and is reproduced on purpose.
+ * Nk must be 32 (z_scale latent tokens); dh in {32, 64}. */
+int ldt_attention_nk32(int B, int H, int Nq, int dh, const void* q, int ldq, const void* k, const void* v,
+                       int ldkv, void* o, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Reverse-SDE predictor updates (diffusion/diffusion_continuous.py:141-191) fused with the score
+ * conversion of Trainer.score_fn (trainer/Latent_SDE_Trainer.py:57-61):  score = -params / sqrt(var)
+ * All arrays [numel] f32.  Per-step scalars come from a device table so the same launch can sit in
+ * a CUDA graph: coef points at 8 floats for this step (see ldt_sde_coef).  Noise: z != NULL uses
+ * caller-provided normals (teacher-forced parity); z == NULL draws Philox4x32-10 normals with
+ * (seed, offset) laid out exactly like torch.randn_like on a CUDA generator.
+ * ------------------------------------------------------------------------------------------------ */
+enum ldt_predictor {
+  LDT_PRED_ANCESTRAL = 0,         /* :152-162 */
+  LDT_PRED_REVERSE_DIFFUSION = 1, /* :141-150 */
+  LDT_PRED_EULER_MARUYAMA = 2,    /* :182-191 */
+  LDT_PRED_DDIM = 3,              /* :164-180 */
+};
+/* coef layout per step (8 floats): [0]=sqrt(var(t)) [1..7] predictor specific, see ldt_b200/sde.py */
+#define LDT_SDE_COEF_STRIDE 8
+
+/* offset_per_step: Philox offset advance per step (what torch adds per randn_like call), so step i of a
+ * replayed CUDA graph uses offset + i*offset_per_step.  rng_grid: number of 256-thread blocks torch would
+ * launch for `numel` elements on this device (<= 0 lets the library pick; only matters when z == NULL). */
+int ldt_sde_step(int predictor, long long numel, const float* x, const float* params, const float* z,
+                 const float* coef_table, const int* step_index /* device int, or NULL = 0 */,
+                 unsigned long long seed, unsigned long long offset, unsigned long long offset_per_step,
+                 int rng_grid, float* x_next, float* x_mean, void* stream);
+
+/* *step_index += 1 (device side), so a captured step graph can be replayed N times. */
+int ldt_advance_step(int* step_index, void* stream);
+
+/* out[0:row_len] = table[*step_index, 0:row_len]  (f32, row_len % 4 == 0).  Used to pull the current
+ * step's AdaLN modulation rows out of the per-timestep table ("batch-invariant AdaLN"). */
+int ldt_select_row(const float* table, long long row_len, const int* step_index, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device properties needed by the host mirror
+ * ------------------------------------------------------------------------------------------------ */
+int ldt_device_sm_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDT_B200_H_ */

@@ -1,0 +1,109 @@
+"""ctypes binding of ``libldt_b200.so`` (the C ABI declared in ``include/ldt_b200.h``).
+
+There is deliberately no fallback: if the library is missing or a call fails, a ``RuntimeError`` is raised.
+PyTorch is used only to own device memory and streams; every pointer crossing this boundary is a raw
+``data_ptr()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libldt_b200.so")
+
+EPI_BIAS_F32 = 0
+EPI_BIAS_BF16 = 1
+EPI_BIAS_GELU_BF16 = 2
+EPI_GATE_RESID_F32 = 3
+
+PRED_ANCESTRAL = 0
+PRED_REVERSE_DIFFUSION = 1
+PRED_EULER_MARUYAMA = 2
+PRED_DDIM = 3
+SDE_COEF_STRIDE = 8
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+        ("A", C.c_void_p), ("lda", C.c_int),
+        ("W", C.c_void_p), ("ldw", C.c_int),
+        ("bias", C.c_void_p),
+        ("out", C.c_void_p), ("ldo", C.c_int),
+        ("epilogue", C.c_int),
+        ("resid", C.c_void_p),
+        ("gate", C.c_void_p),
+        ("gate_stride", C.c_longlong),
+        ("rows_per_gate", C.c_int),
+        ("backend", C.c_int),
+    ]
+
+
+# name -> (restype, argtypes); the single source of truth used by tests to check exported symbols
+PROTOTYPES = {
+    "ldt_abi_version": (C.c_int, []),
+    "ldt_last_error_string": (C.c_char_p, []),
+    "ldt_device_sm_count": (C.c_int, []),
+    "ldt_nn_distance": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldt_pairwise_cd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p]),
+    "ldt_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "ldt_cast_pad_bf16": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "ldt_pack_weights": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "ldt_layernorm_mod_bf16": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,
+                                         C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
+    "ldt_time_embedding": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
+    "ldt_attention_nk32": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                     C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ldt_sde_step": (C.c_int, [C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_void_p]),
+    "ldt_advance_step": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ldt_select_row": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load() -> C.CDLL:
+    """Load the library (once).  Raises RuntimeError with build instructions when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). "
+                "Build it with `python -m ldt_b200.build` (needs nvcc, cross-compiles for sm_100a).")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)  # AttributeError here means header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        if lib.ldt_abi_version() != 1:
+            raise RuntimeError("libldt_b200.so ABI version mismatch; rebuild with `python -m ldt_b200.build --force`")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().ldt_last_error_string().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def stream_ptr(device=None) -> int:
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()

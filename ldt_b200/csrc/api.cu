@@ -1,0 +1,42 @@
+// C-ABI plumbing shared by every entry point: thread-local error string, device attribute cache.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "ldt_b200.h"
+
+namespace ldt {
+
+static thread_local char g_err[1024] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what, const char* file, int line) {
+  if (e == cudaSuccess) return LDT_OK;
+  set_last_error("CUDA error %d (%s) at %s:%d in `%s`", static_cast<int>(e), cudaGetErrorString(e), file, line, what);
+  return LDT_ERR_CUDA;
+}
+
+int num_sms() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = 148;  // B200
+  }
+  return cached;
+}
+
+}  // namespace ldt
+
+extern "C" int ldt_abi_version(void) { return LDT_ABI_VERSION; }
+extern "C" const char* ldt_last_error_string(void) { return ldt::g_err; }
+extern "C" int ldt_device_sm_count(void) { return ldt::num_sms(); }

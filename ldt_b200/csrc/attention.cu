@@ -1,0 +1,209 @@
+// Multi-head attention over the 32 latent tokens: softmax(q k^T / sqrt(dh)) v, one warp per
+// (batch, head, 32-query tile).  Used by the score net (32 queries x 32 keys, dh 64, 16 heads) and by
+// the Compressor decoder (2048 query points x 32 keys, dh 32, 4 heads).
+//
+// Replaces ResidualBlock.compute_attention (model/layers.py:183-200), which the reference runs as
+// permute/clone + bmm + mul + softmax + bmm (9 launches).  The whole score tile (32x32) lives in mma
+// accumulator registers, so no online softmax is needed.  Output layout reproduces the reference's
+// `(w @ v).reshape(B, N, C)` (layers.py:197): result [B,H,Nq,dh] stored contiguously, which the next
+// layer re-reads as token-major [B*Nq, H*dh] without permuting heads back.
+//
+// Tensor-core path: mma.sync.m16n8k16 (bf16 -> fp32).  At 0.5 % of the block's FLOPs and 32-wide tiles
+// this op is bound by moving q/k/v/o (L2-resident), not by tensor throughput; tcgen05's 128-row tiles
+// would idle 3/4 of the array on block-diagonal head structure, so the warp-level MMA is the fit here.
+#include "common.cuh"
+#include "ldt_b200.h"
+
+namespace ldt {
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t ld_u32(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+
+constexpr int ATT_WARPS = 4;
+
+template <int DH>
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attention_nk32_kernel(int units, int H, int Nq, int qtiles, const __nv_bfloat16* __restrict__ q, int ldq,
+                      const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v, int ldkv,
+                      __nv_bfloat16* __restrict__ o, float scale_log2e) {
+  constexpr int VS = DH + 8;  // padded row (elements): 16-byte aligned rows, conflict-free ldmatrix
+  __shared__ __align__(16) __nv_bfloat16 Vs[ATT_WARPS][32 * VS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * ATT_WARPS + warp;
+  if (unit >= units) return;
+  const int qt = unit % qtiles;
+  const int bh = unit / qtiles;
+  const int h = bh % H, b = bh / H;
+  const int g = lane >> 2, t = lane & 3;
+
+  // ---- stage V[32, DH] of this (b, h) ----
+  __nv_bfloat16* vs = Vs[warp];
+  {
+    constexpr int CH = DH / 8;  // 16-byte chunks per row
+    const __nv_bfloat16* vb = v + static_cast<size_t>(b) * 32 * ldkv + h * DH;
+    for (int i = lane; i < 32 * CH; i += 32) {
+      const int key = i / CH, c = i % CH;
+      *reinterpret_cast<uint4*>(vs + key * VS + c * 8) =
+          *reinterpret_cast<const uint4*>(vb + static_cast<size_t>(key) * ldkv + c * 8);
+    }
+  }
+  __syncwarp();
+
+  // ---- S = Q K^T ----
+  const int n_base = qt * 32;
+  float s[2][4][4];
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[mi][ni][e] = 0.f;
+  {
+    const __nv_bfloat16* qb = q + static_cast<size_t>(b) * Nq * ldq + h * DH;
+    const __nv_bfloat16* qrow[2][2];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      qrow[mi][0] = qb + static_cast<size_t>(min(n_base + mi * 16 + g, Nq - 1)) * ldq;
+      qrow[mi][1] = qb + static_cast<size_t>(min(n_base + mi * 16 + g + 8, Nq - 1)) * ldq;
+    }
+    const __nv_bfloat16* kb = k + static_cast<size_t>(b) * 32 * ldkv + h * DH;
+#pragma unroll
+    for (int ks = 0; ks < DH / 16; ++ks) {
+      uint32_t a[2][4];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        a[mi][0] = ld_u32(qrow[mi][0] + ks * 16 + 2 * t);
+        a[mi][1] = ld_u32(qrow[mi][1] + ks * 16 + 2 * t);
+        a[mi][2] = ld_u32(qrow[mi][0] + ks * 16 + 2 * t + 8);
+        a[mi][3] = ld_u32(qrow[mi][1] + ks * 16 + 2 * t + 8);
+      }
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const __nv_bfloat16* krow = kb + static_cast<size_t>(ni * 8 + g) * ldkv + ks * 16 + 2 * t;
+        const uint32_t b0 = ld_u32(krow), b1 = ld_u32(krow + 8);
+        mma_bf16_16816(s[0][ni], a[0], b0, b1);
+        mma_bf16_16816(s[1][ni], a[1], b0, b1);
+      }
+    }
+  }
+
+  // ---- softmax over the 32 keys (rows g and g+8 of each 16-row tile) ----
+  float inv_sum[2][2];
+  uint32_t pfrag[2][2][4];
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi) {
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      float m = -INFINITY;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) m = fmaxf(m, fmaxf(s[mi][ni][2 * hh], s[mi][ni][2 * hh + 1]));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const float p0 = exp2f((s[mi][ni][2 * hh] - m) * scale_log2e);
+        const float p1 = exp2f((s[mi][ni][2 * hh + 1] - m) * scale_log2e);
+        s[mi][ni][2 * hh] = p0;
+        s[mi][ni][2 * hh + 1] = p1;
+        sum += p0 + p1;
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      inv_sum[mi][hh] = 1.0f / sum;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      pfrag[mi][j][0] = pack_bf16(s[mi][2 * j][0], s[mi][2 * j][1]);
+      pfrag[mi][j][1] = pack_bf16(s[mi][2 * j][2], s[mi][2 * j][3]);
+      pfrag[mi][j][2] = pack_bf16(s[mi][2 * j + 1][0], s[mi][2 * j + 1][1]);
+      pfrag[mi][j][3] = pack_bf16(s[mi][2 * j + 1][2], s[mi][2 * j + 1][3]);
+    }
+  }
+
+  // ---- O = P V ----
+  __nv_bfloat16* ob = o + (static_cast<size_t>(bh) * Nq) * DH;
+  const int mat = lane >> 3, r8 = lane & 7;
+#pragma unroll
+  for (int np = 0; np < DH / 16; ++np) {  // pairs of 8-wide output tiles
+    float acc[2][2][4];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int nn = 0; nn < 2; ++nn)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[mi][nn][e] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      uint32_t r0, r1, r2, r3;
+      const __nv_bfloat16* addr = vs + (16 * j + (mat & 1) * 8 + r8) * VS + (2 * np + (mat >> 1)) * 8;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                   : "r"(smem_u32(addr)));
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        mma_bf16_16816(acc[mi][0], pfrag[mi][j], r0, r1);
+        mma_bf16_16816(acc[mi][1], pfrag[mi][j], r2, r3);
+      }
+    }
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int nn = 0; nn < 2; ++nn) {
+        const int col = (2 * np + nn) * 8 + 2 * t;
+        const int n0 = n_base + mi * 16 + g;
+        if (n0 < Nq)
+          *reinterpret_cast<uint32_t*>(ob + static_cast<size_t>(n0) * DH + col) =
+              pack_bf16(acc[mi][nn][0] * inv_sum[mi][0], acc[mi][nn][1] * inv_sum[mi][0]);
+        if (n0 + 8 < Nq)
+          *reinterpret_cast<uint32_t*>(ob + static_cast<size_t>(n0 + 8) * DH + col) =
+              pack_bf16(acc[mi][nn][2] * inv_sum[mi][1], acc[mi][nn][3] * inv_sum[mi][1]);
+      }
+  }
+}
+
+}  // namespace ldt
+
+using namespace ldt;
+
+extern "C" int ldt_attention_nk32(int B, int H, int Nq, int dh, const void* q, int ldq, const void* k, const void* v,
+                                  int ldkv, void* o, void* stream) {
+  LDT_REQUIRE(B >= 0 && H > 0 && Nq > 0, LDT_ERR_INVALID, "ldt_attention_nk32: bad shape B=%d H=%d Nq=%d", B, H, Nq);
+  LDT_REQUIRE(dh == 32 || dh == 64, LDT_ERR_UNSUPPORTED, "ldt_attention_nk32: head dim %d not in {32,64}", dh);
+  if (B == 0) return LDT_OK;
+  LDT_REQUIRE(q && k && v && o, LDT_ERR_INVALID, "ldt_attention_nk32: null pointer");
+  LDT_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && ldq >= H * dh && ldkv >= H * dh, LDT_ERR_INVALID,
+              "ldt_attention_nk32: ldq=%d ldkv=%d must be multiples of 8 and >= H*dh", ldq, ldkv);
+  LDT_REQUIRE((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+               reinterpret_cast<uintptr_t>(o)) % 16 == 0,
+              LDT_ERR_INVALID, "ldt_attention_nk32: pointers must be 16-byte aligned");
+  const int qtiles = (Nq + 31) / 32;
+  const long long units = static_cast<long long>(B) * H * qtiles;
+  LDT_REQUIRE(units < (1LL << 31), LDT_ERR_INVALID, "ldt_attention_nk32: too many work units");
+  const int grid = static_cast<int>((units + ATT_WARPS - 1) / ATT_WARPS);
+  const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(dh));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dh == 64)
+    attention_nk32_kernel<64><<<grid, ATT_WARPS * 32, 0, s>>>(static_cast<int>(units), H, Nq, qtiles,
+                                                             static_cast<const __nv_bfloat16*>(q), ldq,
+                                                             static_cast<const __nv_bfloat16*>(k),
+                                                             static_cast<const __nv_bfloat16*>(v), ldkv,
+                                                             static_cast<__nv_bfloat16*>(o), scale_log2e);
+  else
+    attention_nk32_kernel<32><<<grid, ATT_WARPS * 32, 0, s>>>(static_cast<int>(units), H, Nq, qtiles,
+                                                             static_cast<const __nv_bfloat16*>(q), ldq,
+                                                             static_cast<const __nv_bfloat16*>(k),
+                                                             static_cast<const __nv_bfloat16*>(v), ldkv,
+                                                             static_cast<__nv_bfloat16*>(o), scale_log2e);
+  LDT_CUDA_OK(cudaGetLastError());
+  return LDT_OK;
+}

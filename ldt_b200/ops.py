@@ -1,0 +1,142 @@
+"""Tensor-level wrappers over the C ABI.  Each function validates what the reference's CHECK_INPUT macro
+validates (CUDA + contiguous, evaluation/pytorch_structural_losses/src/structural_loss.cpp:10-12), allocates
+outputs with torch (caller-owned memory; the kernels never allocate) and launches on the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_GATE_RESID_F32, GemmArgs, check, load,
+                   ptr, stream_ptr)
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def nn_distance_idx(a: torch.Tensor, b: torch.Tensor):
+    """(dist1, idx1, dist2, idx2) -- StructuralLossesBackend.NNDistance (structural_loss.cpp:80-99)."""
+    _req(a, torch.float32, "set_d")
+    _req(b, torch.float32, "set_q")
+    if a.dim() != 3 or b.dim() != 3 or a.shape[2] != 3 or b.shape[2] != 3 or a.shape[0] != b.shape[0]:
+        raise RuntimeError(f"expected [b,n,3] and [b,m,3], got {tuple(a.shape)} and {tuple(b.shape)}")
+    bs, n, m = a.shape[0], a.shape[1], b.shape[1]
+    dist1 = torch.empty((bs, n), dtype=torch.float32, device=a.device)
+    idx1 = torch.empty((bs, n), dtype=torch.int32, device=a.device)
+    dist2 = torch.empty((bs, m), dtype=torch.float32, device=a.device)
+    idx2 = torch.empty((bs, m), dtype=torch.int32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(load().ldt_nn_distance(bs, n, ptr(a), m, ptr(b), ptr(dist1), ptr(idx1), ptr(dist2), ptr(idx2),
+                                     stream_ptr()), "ldt_nn_distance")
+    return dist1, idx1, dist2, idx2
+
+
+def pairwise_cd(a: torch.Tensor, b: torch.Tensor, row_begin: int = 0, row_end: int | None = None) -> torch.Tensor:
+    """Rows [row_begin,row_end) of the [na,nb] Chamfer matrix between cloud sets a [na,pa,3] and b [nb,pb,3]."""
+    _req(a, torch.float32, "a")
+    _req(b, torch.float32, "b")
+    if a.dim() != 3 or b.dim() != 3 or a.shape[2] != 3 or b.shape[2] != 3:
+        raise RuntimeError(f"expected [na,pa,3] and [nb,pb,3], got {tuple(a.shape)} and {tuple(b.shape)}")
+    na, pa = a.shape[0], a.shape[1]
+    nb, pb = b.shape[0], b.shape[1]
+    row_end = na if row_end is None else row_end
+    out = torch.empty((row_end - row_begin, nb), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(load().ldt_pairwise_cd(na, nb, pa, pb, ptr(a), ptr(b), row_begin, row_end, ptr(out), stream_ptr()),
+              "ldt_pairwise_cd")
+    return out
+
+
+def gemm(A: torch.Tensor, W: torch.Tensor, bias, out: torch.Tensor, epilogue: int, *, N: int | None = None,
+         K: int | None = None, resid=None, gate=None, gate_stride: int = 0, rows_per_gate: int = 1,
+         backend: int = 0) -> torch.Tensor:
+    """out = epilogue(A @ W[:N,:K].T + bias).  A bf16 [M, lda], W bf16 [>=N, ldw]; strides taken from tensors."""
+    assert A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16 and A.dim() == 2 and W.dim() == 2
+    assert A.stride(1) == 1 and W.stride(1) == 1 and out.stride(-1) == 1
+    M = A.shape[0]
+    K = A.shape[1] if K is None else K
+    N = W.shape[0] if N is None else N
+    out2 = out.view(-1, out.shape[-1]) if out.dim() != 2 else out
+    args = GemmArgs(M=M, N=N, K=K, A=ptr(A), lda=A.stride(0), W=ptr(W), ldw=W.stride(0), bias=ptr(bias),
+                    out=ptr(out2), ldo=out2.stride(0), epilogue=epilogue, resid=ptr(resid), gate=ptr(gate),
+                    gate_stride=gate_stride, rows_per_gate=rows_per_gate, backend=backend)
+    with torch.cuda.device(A.device):
+        check(load().ldt_gemm_bf16(C.byref(args), stream_ptr()), "ldt_gemm_bf16")
+    return out
+
+
+def cast_pad_bf16(x: torch.Tensor, ld_out: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """f32 [rows, cols] -> bf16 [rows, ld_out] zero-padded."""
+    _req(x, torch.float32, "x")
+    x2 = x.view(-1, x.shape[-1])
+    rows, cols = x2.shape
+    if out is None:
+        out = torch.empty((rows, ld_out), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(load().ldt_cast_pad_bf16(rows, cols, ptr(x2), x2.stride(0), ptr(out), ld_out, stream_ptr()),
+              "ldt_cast_pad_bf16")
+    return out
+
+
+def pack_weight(w: torch.Tensor, ld_out: int | None = None) -> torch.Tensor:
+    """Conv1d(k=1)/Linear weight [out, in(,1)] f32 -> bf16 [out, ld_out] K-major, zero-padded to a multiple of 64."""
+    w2 = w.detach().reshape(w.shape[0], -1).contiguous().float()
+    rows, cols = w2.shape
+    ld_out = ((cols + 63) // 64) * 64 if ld_out is None else ld_out
+    out = torch.empty((rows, ld_out), dtype=torch.bfloat16, device=w.device)
+    with torch.cuda.device(w.device):
+        check(load().ldt_pack_weights(rows, cols, ptr(w2), cols, ptr(out), ld_out, stream_ptr()), "ldt_pack_weights")
+    return out
+
+
+def layernorm_mod(x: torch.Tensor, out: torch.Tensor, *, shift=None, scale=None, mod_stride: int = 0,
+                  rows_per_mod: int = 1, weight=None, bias=None, eps: float = 1e-6) -> torch.Tensor:
+    rows, Cc = x.shape
+    with torch.cuda.device(x.device):
+        check(load().ldt_layernorm_mod_bf16(rows, Cc, ptr(x), ptr(shift), ptr(scale), mod_stride, rows_per_mod,
+                                            ptr(weight), ptr(bias), eps, ptr(out), stream_ptr()),
+              "ldt_layernorm_mod_bf16")
+    return out
+
+
+def time_embedding(t, freq, w0, b0, w1, b1, extra, c_out, silu_out, scratch) -> None:
+    R, half, D = t.shape[0], freq.shape[0], w1.shape[0]
+    with torch.cuda.device(t.device):
+        check(load().ldt_time_embedding(R, half, D, ptr(t), ptr(freq), ptr(w0), ptr(b0), ptr(w1), ptr(b1), ptr(extra),
+                                        ptr(c_out), ptr(silu_out), ptr(scratch), stream_ptr()), "ldt_time_embedding")
+
+
+def attention_nk32(B: int, H: int, Nq: int, dh: int, q, ldq: int, k, v, ldkv: int, o) -> None:
+    with torch.cuda.device(o.device):
+        check(load().ldt_attention_nk32(B, H, Nq, dh, ptr(q), ldq, ptr(k), ptr(v), ldkv, ptr(o), stream_ptr()),
+              "ldt_attention_nk32")
+
+
+def sde_step(predictor: int, x, params, z, coef_table, step_index, seed: int, offset: int, offset_per_step: int,
+             rng_grid: int, x_next, x_mean) -> None:
+    with torch.cuda.device(x.device):
+        check(load().ldt_sde_step(predictor, x.numel(), ptr(x), ptr(params), ptr(z), ptr(coef_table), ptr(step_index),
+                                  seed, offset, offset_per_step, rng_grid, ptr(x_next), ptr(x_mean), stream_ptr()),
+              "ldt_sde_step")
+
+
+def advance_step(step_index) -> None:
+    with torch.cuda.device(step_index.device):
+        check(load().ldt_advance_step(ptr(step_index), stream_ptr()), "ldt_advance_step")
+
+
+def select_row(table, step_index, out) -> None:
+    with torch.cuda.device(out.device):
+        check(load().ldt_select_row(ptr(table), table.shape[1], ptr(step_index), ptr(out), stream_ptr()),
+              "ldt_select_row")
+
+
+__all__ = [n for n in dir() if not n.startswith("_")] + ["_lib"]

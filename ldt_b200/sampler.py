@@ -1,0 +1,133 @@
+"""The fused reverse-SDE loop: N steps of (score net -> predictor update -> noise) as one replayed CUDA graph.
+
+Replaces the Python ``pc_sampling`` loop of the reference (diffusion/diffusion_continuous.py:231-258), which
+issues ~700 kernel launches per step.  Three things make one captured step replayable N times:
+
+* every per-step scalar lives in a device table indexed by a device-side step counter (``ldt_sde_step``,
+  ``ldt_advance_step``);
+* in unconditional sampling every sample shares the step's time value, so TimeEmbedding and all 25 adaLN
+  projections are batch-invariant: they are computed for ALL N timesteps up front as one GEMM
+  ([N, t_dim] x [t_dim, 6*hidden*blocks + 2*hidden]) and each step just selects its row (``ldt_select_row``);
+* the per-step noise is generated inside the update kernel with the Philox counter layout of
+  ``torch.randn_like`` on the CUDA default generator, and the generator offset is advanced afterwards by what
+  the reference would have consumed, so the stream position seen by later torch calls matches.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .sde import _PRED_CODES, torch_randn_launch_geometry
+
+
+def find_score_module(score_fn, sde):
+    """Return the ldt_b200.Score behind a Trainer.score_fn closure (trainer/Latent_SDE_Trainer.py:57-61), or None.
+
+    The fused loop hard-wires ``score = -params / sqrt(SDE.var(t))``; it is only taken when the callable is a bound
+    method named ``score_fn`` of an object whose ``.model`` is our Score and whose ``.SDE`` is this SDE object.
+    """
+    from .score import Score
+    owner = getattr(score_fn, "__self__", None)
+    if owner is None or getattr(score_fn, "__name__", "") != "score_fn":
+        return None
+    model = getattr(owner, "model", None)
+    if isinstance(model, Score) and getattr(owner, "SDE", None) is sde:
+        return model
+    return None
+
+
+def modulation_table(score, P, timesteps: torch.Tensor, chunk: int = 256) -> torch.Tensor:
+    """AdaLN rows for every timestep: f32 [N, 6*hidden*blocks + 2*hidden]."""
+    N = timesteps.shape[0]
+    dev = timesteps.device
+    half = (score.t_dim // 4) // 2
+    mod_len = score.num_blocks * 6 * score.hidden_size + 2 * score.hidden_size
+    table = torch.empty((N, mod_len), dtype=torch.float32, device=dev)
+    w0, b0, w1, b1 = P["te"]
+    for s in range(0, N, chunk):
+        e = min(N, s + chunk)
+        R = e - s
+        c = torch.empty((R, score.hidden_size), dtype=torch.float32, device=dev)
+        sc = torch.empty((R, score.hidden_size), dtype=torch.bfloat16, device=dev)
+        scratch = torch.empty((R, score.hidden_size + 2 * half), dtype=torch.float32, device=dev)
+        ops.time_embedding(timesteps[s:e].contiguous(), P["freq"], w0, b0, w1, b1, None, c, sc, scratch)
+        ops.gemm(sc, P["w_ada"], P["b_ada"], table[s:e], ops.EPI_BIAS_F32)
+    return table
+
+
+class StepGraph:
+    """One captured sampler step, replayable; owns the loop state buffers."""
+
+    def __init__(self, score, sde, B, N, predictor, time_eps, probability_flow, device, use_graph=True):
+        self.score, self.B, self.N = score, B, N
+        P = score.packed()
+        self.P = P
+        self.coef, self.timesteps = sde.step_coefficients(predictor, N, time_eps, probability_flow, device)
+        self.table = modulation_table(score, P, self.timesteps)
+        self.ws = score._workspace(B, 1, device)
+        self.code = _PRED_CODES[predictor]
+        T, D = score.z_scale, score.z_dim
+        self.x = torch.empty((B, T, D), dtype=torch.float32, device=device)
+        self.x_mean = torch.empty_like(self.x)
+        self.params = torch.empty_like(self.x)
+        self.step = torch.zeros(1, dtype=torch.int32, device=device)
+        self.mod_cur = torch.empty((1, self.table.shape[1]), dtype=torch.float32, device=device)
+        self.rng_grid, self.offset_per_step = torch_randn_launch_geometry(self.x.numel(), device)
+        self.seed = 0
+        self.offset = 0
+        self.graph = None
+        self.use_graph = use_graph
+
+    def _step_body(self):
+        B, T, D = self.x.shape
+        ops.select_row(self.table, self.step, self.mod_cur)
+        self.score.run_tokens(self.P, self.ws, self.x.view(B * T, D), self.mod_cur, 0, self.params.view(B * T, D))
+        ops.sde_step(self.code, self.x, self.params, None, self.coef, self.step, self.seed, self.offset,
+                     self.offset_per_step, self.rng_grid, self.x, self.x_mean)
+        ops.advance_step(self.step)
+
+    def run(self, x0: torch.Tensor, seed: int, offset: int) -> None:
+        """Run all N steps from x0 (copied into the loop buffer) with Philox (seed, offset)."""
+        self.x.copy_(x0)
+        self.step.zero_()
+        if not self.use_graph:
+            self.seed, self.offset = seed, offset
+            for _ in range(self.N):
+                self._step_body()
+            return
+        if self.graph is None or (seed, offset) != (self.seed, self.offset):
+            # seed/offset are baked into the captured kernel arguments: (re)capture for a new generator position
+            self.seed, self.offset = seed, offset
+            self._step_body()  # warm-up outside capture (lazy module loading, attribute setup)
+            self.x.copy_(x0)
+            self.step.zero_()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_body()
+            self.graph = g
+            # the capture itself does not execute; state is still (x0, step 0)
+        for _ in range(self.N):
+            self.graph.replay()
+
+
+_graph_cache: dict = {}
+
+
+def fused_sample_loop(score, sde, x0, N, predictor, time_eps, probability_flow, denoise, use_graph=True):
+    """x0 [B, z_scale, z_dim] on the device -> latent after N reverse steps (x_mean if denoise else x)."""
+    device = x0.device
+    B = x0.shape[0]
+    key = (id(score), id(sde), B, N, predictor, float(time_eps), bool(probability_flow), device, use_graph,
+           score._fingerprint())
+    sg = _graph_cache.get(key)
+    if sg is None:
+        _graph_cache.clear()  # one live plan: the buffers are large (modulation table ~0.6 GB at N=1000)
+        sg = StepGraph(score, sde, B, N, predictor, time_eps, probability_flow, device, use_graph)
+        _graph_cache[key] = sg
+    gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+    seed, offset = gen.initial_seed(), gen.get_offset()
+    sg.run(x0, seed, offset)
+    # the reference draws one randn_like per step from this generator (:160); leave it where it would be
+    gen.set_offset(offset + N * sg.offset_per_step)
+    return (sg.x_mean if denoise else sg.x).clone()

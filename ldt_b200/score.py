@@ -1,0 +1,312 @@
+"""Host mirror of the reference score network ``Score`` (reference model/scorenet/score.py:47-151).
+
+Same constructor keys (``cfg.score``), same ``forward(x, t, label=None, condition=None)`` signature and the
+same ``state_dict`` layout (``Transformer.{i}.{fc_q,fc_kv,fc_o}.*``, ``Transformer.{i}.adaLN.1.*``,
+``Transformer.{i}.mlp.{fc.0.0,out}.*``, ``ln_in.*``, ``TimeEmbedding.mlp.{0,2}.*``, ``ln_out.{adaLN.1,ln}.*``),
+so reference checkpoints load with ``strict=True``.  Parameters are ordinary fp32 ``nn.Parameter``s; the
+arithmetic runs in the sm_100a kernels behind ``libldt_b200.so``:
+
+  token-major activations [B*32, C]  (the reference is channels-first [B, C, 32]; a layout choice only)
+  per block:  LN+AdaLN-modulate (1 pass) -> fused QKV tcgen05 GEMM -> 32-token MHA -> fc_o GEMM with
+              gate*acc+residual epilogue -> LN+modulate -> fc GEMM with GELU epilogue -> out GEMM with
+              gate*acc+residual epilogue            (reference: ~28 launches per block, model/layers.py:202-229)
+
+There is no PyTorch fallback for the arithmetic: without the CUDA library ``forward`` raises.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_GATE_RESID_F32
+
+TOKENS_PAD = 64  # K padding granule of the GEMM core
+
+
+class _MLPParams(nn.Module):
+    """Parameter holder laid out like reference MLP(n_hidden=1): fc.0.0 and out (model/layers.py:110-124)."""
+
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc = nn.ModuleList([nn.Sequential(nn.Conv1d(dim, hidden, 1))])
+        self.out = nn.Conv1d(hidden, dim, 1)
+
+
+class _AdaLNBlockParams(nn.Module):
+    """Parameter holder for one AdaLN ResidualBlock with dim_in == dim_out (model/layers.py:140-181)."""
+
+    def __init__(self, dim, dim_kv, dim_c, mlp_ratio=4.0):
+        super().__init__()
+        self.fc_q = nn.Conv1d(dim, dim, 1)
+        self.fc_kv = nn.Conv1d(dim_kv, 2 * dim, 1)
+        self.fc_o = nn.Conv1d(dim, dim, 1)
+        self.adaLN = nn.Sequential(nn.SiLU(), nn.Linear(dim_c, 6 * dim))
+        self.mlp = _MLPParams(dim, int(mlp_ratio * dim))
+
+
+class _TimeEmbeddingParams(nn.Module):
+    def __init__(self, dim_embed, dim_out):
+        super().__init__()
+        self.mlp = nn.Sequential(nn.Linear(dim_embed, dim_out), nn.SiLU(), nn.Linear(dim_out, dim_out))
+        self.t_emb_dim = dim_embed
+
+
+class _LabelEmbeddingParams(nn.Module):
+    def __init__(self, num_categorys, dim_embed, dim_out):
+        super().__init__()
+        self.label_emb = nn.Embedding(num_categorys, dim_embed)
+        self.mlp = nn.Sequential(nn.Linear(dim_embed, dim_out), nn.SiLU(), nn.Linear(dim_out, dim_out))
+
+    def forward(self, label):  # per-sample prologue (once per sample() call), plain torch
+        return self.mlp(self.label_emb(label))
+
+
+class _FinalLayerParams(nn.Module):
+    def __init__(self, dim_in, dim_out, dim_c):
+        super().__init__()
+        self.adaLN = nn.Sequential(nn.SiLU(), nn.Linear(dim_c, 2 * dim_in))
+        self.ln = nn.Conv1d(dim_in, dim_out, 1)
+
+
+def _pad_to(n: int, g: int) -> int:
+    return (n + g - 1) // g * g
+
+
+class _Workspace:
+    """Caller-owned device buffers for one batch size (the kernels never allocate)."""
+
+    def __init__(self, B, tokens, z_dim, hidden, n_blocks, mod_rows, half, device):
+        M = B * tokens
+        bf, f32 = torch.bfloat16, torch.float32
+        self.B, self.M = B, M
+        self.mod_len = n_blocks * 6 * hidden + 2 * hidden
+        self.xa = torch.zeros((M, _pad_to(z_dim, 64)), dtype=bf, device=device)
+        self.h = torch.empty((M, hidden), dtype=f32, device=device)
+        self.a = torch.empty((M, hidden), dtype=bf, device=device)
+        self.qkv = torch.empty((M, 3 * hidden), dtype=bf, device=device)
+        self.att = torch.empty((M, hidden), dtype=bf, device=device)
+        self.hid = torch.empty((M, 4 * hidden), dtype=bf, device=device)
+        self.set_mod_rows(mod_rows, hidden, half, device)
+
+    def set_mod_rows(self, R, hidden, half, device):
+        self.R = R
+        self.c = torch.empty((R, hidden), dtype=torch.float32, device=device)
+        self.sc = torch.zeros((R, hidden), dtype=torch.bfloat16, device=device)
+        self.mod = torch.empty((R, self.mod_len), dtype=torch.float32, device=device)
+        self.scratch = torch.empty((R, hidden + 2 * half), dtype=torch.float32, device=device)
+
+
+class Score(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.z_dim = cfg.z_dim
+        self.out_dim = self.z_dim
+        self.z_scale = cfg.z_scale
+        self.hidden_size = cfg.hidden_size
+        self.num_heads = cfg.num_heads
+        self.condition = cfg.condition
+        self.num_steps = cfg.num_steps
+        self.norm = cfg.norm
+        self.t_dim = cfg.t_dim
+        self.num_blocks = cfg.num_blocks
+        self.dropout = cfg.dropout
+        self.learn_sigma = cfg.learn_sigma
+        self.unet = cfg.unet
+        self.AdaLN = cfg.AdaLN
+        if self.unet:
+            raise NotImplementedError("ldt_b200.Score: the unet variant (score.py:67-83) is not on the B200 hot path yet")
+        if not self.AdaLN:
+            raise NotImplementedError("ldt_b200.Score: only AdaLN blocks (the shipped configs) are supported")
+        if self.norm != "layer_norm":
+            raise NotImplementedError("ldt_b200.Score: only norm: layer_norm (the shipped configs) is supported")
+        if self.dropout != 0:
+            raise NotImplementedError("ldt_b200.Score is a sampling path: dropout must be 0")
+        if self.condition:
+            raise NotImplementedError(
+                "ldt_b200.Score: the ConditionNet prologue (score.py:13-44) is not built yet; pass precomputed "
+                "condition tokens as condition=(pts_cond, img_cond) to a model built with condition: False")
+        if self.hidden_size % 128 != 0 or self.hidden_size // self.num_heads not in (32, 64) or self.z_scale != 32:
+            raise NotImplementedError("ldt_b200.Score: needs hidden_size % 128 == 0, head dim 32 or 64, z_scale 32")
+        # construction order follows score.py:84-97 (blocks, label embedding, ln_in, time embedding, final layer)
+        self.Transformer = nn.ModuleList(
+            [_AdaLNBlockParams(self.hidden_size, self.hidden_size, self.t_dim) for _ in range(self.num_blocks)])
+        if cfg.num_categorys > 1:
+            self.LabelEmbedding = _LabelEmbeddingParams(cfg.num_categorys, self.t_dim, self.t_dim)
+        else:
+            self.label_dim = None
+        self.ln_in = nn.Conv1d(self.z_dim, self.hidden_size, 1)
+        self.TimeEmbedding = _TimeEmbeddingParams(self.t_dim // 4, self.t_dim)
+        self.ln_out = _FinalLayerParams(self.hidden_size, self.z_dim, self.t_dim)
+        self._packed = None
+        self._packed_key = None
+        self._ws = {}
+
+    # ------------------------------------------------------------------------------------------
+    # weight packing (fp32 parameters -> bf16 K-major GEMM operands), invalidated when any parameter's
+    # storage or version changes (EMA.swap_parameters_with_ema replaces p.data, tools/utils.py:80-101)
+    # ------------------------------------------------------------------------------------------
+    def _fingerprint(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def packed(self):
+        key = self._fingerprint()
+        if self._packed is not None and key == self._packed_key:
+            return self._packed
+        dev = self.ln_in.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("ldt_b200.Score runs on CUDA only (no CPU fallback); call .to('cuda') first")
+        P = {}
+        with torch.no_grad():
+            P["w_in"] = ops.pack_weight(self.ln_in.weight)
+            P["b_in"] = self.ln_in.bias.detach().float().contiguous()
+            P["blocks"] = []
+            ada_w, ada_b = [], []
+            for blk in self.Transformer:
+                wq = torch.cat([blk.fc_q.weight.detach().reshape(self.hidden_size, -1),
+                                blk.fc_kv.weight.detach().reshape(2 * self.hidden_size, -1)], dim=0)
+                d = {
+                    "w_qkv": ops.pack_weight(wq),
+                    "b_qkv": torch.cat([blk.fc_q.bias.detach(), blk.fc_kv.bias.detach()]).float().contiguous(),
+                    "w_o": ops.pack_weight(blk.fc_o.weight), "b_o": blk.fc_o.bias.detach().float().contiguous(),
+                    "w_fc1": ops.pack_weight(blk.mlp.fc[0][0].weight),
+                    "b_fc1": blk.mlp.fc[0][0].bias.detach().float().contiguous(),
+                    "w_fc2": ops.pack_weight(blk.mlp.out.weight), "b_fc2": blk.mlp.out.bias.detach().float().contiguous(),
+                }
+                P["blocks"].append(d)
+                ada_w.append(blk.adaLN[1].weight.detach())
+                ada_b.append(blk.adaLN[1].bias.detach())
+            ada_w.append(self.ln_out.adaLN[1].weight.detach())
+            ada_b.append(self.ln_out.adaLN[1].bias.detach())
+            P["w_ada"] = ops.pack_weight(torch.cat(ada_w, dim=0))
+            P["b_ada"] = torch.cat(ada_b).float().contiguous()
+            P["w_out"] = ops.pack_weight(self.ln_out.ln.weight)
+            P["b_out"] = self.ln_out.ln.bias.detach().float().contiguous()
+            te = self.TimeEmbedding.mlp
+            P["te"] = tuple(t.detach().float().contiguous() for t in (te[0].weight, te[0].bias, te[2].weight, te[2].bias))
+            half = (self.t_dim // 4) // 2
+            # frequencies exactly as TimeEmbedding.calc_t_emb builds them (model/layers.py:27-30)
+            P["freq"] = torch.exp(torch.arange(half) * -(np.log(10000) / (half - 1))).to(dev)
+        self._packed, self._packed_key = P, key
+        return P
+
+    def _workspace(self, B, mod_rows, device):
+        half = (self.t_dim // 4) // 2
+        ws = self._ws.get(B)
+        if ws is None or ws.h.device != device:
+            ws = _Workspace(B, self.z_scale, self.z_dim, self.hidden_size, self.num_blocks, mod_rows, half, device)
+            self._ws[B] = ws
+        elif ws.R != mod_rows:
+            ws.set_mod_rows(mod_rows, self.hidden_size, half, device)
+        return ws
+
+    # ------------------------------------------------------------------------------------------
+    def modulation(self, P, ws, t, extra=None):
+        """c = TimeEmbedding(t) (+ extra); mod = adaLN_all(SiLU(c))  ->  ws.mod [R, 6*hidden*blocks + 2*hidden].
+
+        Replaces TimeEmbedding.forward plus the 25 per-layer ``adaLN(c)`` Linear calls (layers.py:214,243): they all
+        consume the same SiLU(c), so they are one GEMM against the row-concatenated adaLN weights.
+        """
+        w0, b0, w1, b1 = P["te"]
+        ops.time_embedding(t, P["freq"], w0, b0, w1, b1, extra, ws.c, ws.sc, ws.scratch)
+        ops.gemm(ws.sc, P["w_ada"], P["b_ada"], ws.mod, EPI_BIAS_F32)
+        return ws.mod
+
+    def run_tokens(self, P, ws, x_tokens, mod, mod_stride, out, kv_cond=None):
+        """The per-step token path: x_tokens f32 [M, z_dim] -> out f32 [M, z_dim].  ``mod`` holds the AdaLN
+        rows (one row broadcast when mod_stride == 0, else one per sample)."""
+        Hd, T = self.hidden_size, self.z_scale
+        B = ws.B
+        heads, dh = self.num_heads, Hd // self.num_heads
+        mp = mod.data_ptr()
+
+        def mview(off):  # pointer to a 1024-wide modulation chunk
+            return _PtrView(mp + 4 * off)
+
+        ops.cast_pad_bf16(x_tokens, ws.xa.shape[1], out=ws.xa)
+        ops.gemm(ws.xa, P["w_in"], P["b_in"], ws.h, EPI_BIAS_F32)
+        q = ws.qkv
+        k = _PtrView(ws.qkv.data_ptr() + 2 * Hd)
+        v = _PtrView(ws.qkv.data_ptr() + 4 * Hd)
+        for i, W in enumerate(P["blocks"]):
+            base = i * 6 * Hd
+            ops.layernorm_mod(ws.h, ws.a, shift=mview(base), scale=mview(base + Hd), mod_stride=mod_stride, rows_per_mod=T)
+            if kv_cond is not None and i % 2 == 0:
+                # cross-attention to the (step-invariant) condition tokens: only Q is projected per step
+                ops.gemm(ws.a, W["w_qkv"], W["b_qkv"], ws.qkv, EPI_BIAS_BF16, N=Hd)
+                kc = kv_cond[i // 2]
+                ops.attention_nk32(B, heads, T, dh, q, 3 * Hd, kc, _PtrView(kc.data_ptr() + 2 * Hd), 2 * Hd, ws.att)
+            else:
+                ops.gemm(ws.a, W["w_qkv"], W["b_qkv"], ws.qkv, EPI_BIAS_BF16)
+                ops.attention_nk32(B, heads, T, dh, q, 3 * Hd, k, v, 3 * Hd, ws.att)
+            ops.gemm(ws.att, W["w_o"], W["b_o"], ws.h, EPI_GATE_RESID_F32, resid=ws.h, gate=mview(base + 2 * Hd),
+                     gate_stride=mod_stride, rows_per_gate=T)
+            ops.layernorm_mod(ws.h, ws.a, shift=mview(base + 3 * Hd), scale=mview(base + 4 * Hd), mod_stride=mod_stride,
+                              rows_per_mod=T)
+            ops.gemm(ws.a, W["w_fc1"], W["b_fc1"], ws.hid, EPI_BIAS_GELU_BF16)
+            ops.gemm(ws.hid, W["w_fc2"], W["b_fc2"], ws.h, EPI_GATE_RESID_F32, resid=ws.h, gate=mview(base + 5 * Hd),
+                     gate_stride=mod_stride, rows_per_gate=T)
+        base = self.num_blocks * 6 * Hd
+        ops.layernorm_mod(ws.h, ws.a, shift=mview(base), scale=mview(base + Hd), mod_stride=mod_stride, rows_per_mod=T)
+        ops.gemm(ws.a, P["w_out"], P["b_out"], out, EPI_BIAS_F32, N=self.z_dim)
+        return out
+
+    def project_condition_tokens(self, P, cond_tokens):
+        """K/V of the fixed condition tokens for every even block, computed once per sample() call
+        (score.py:148-149 re-projects them every step; they do not depend on the step)."""
+        B = cond_tokens.shape[0]
+        Hd = self.hidden_size
+        y = cond_tokens.transpose(1, 2).contiguous().view(B * self.z_scale, Hd).float()
+        ya = ops.cast_pad_bf16(y, Hd)
+        out = []
+        for i, W in enumerate(P["blocks"]):
+            if i % 2 == 0:
+                kv = torch.empty((B * self.z_scale, 2 * Hd), dtype=torch.bfloat16, device=y.device)
+                wkv = W["w_qkv"][Hd:]
+                ops.gemm(ya, wkv, W["b_qkv"][Hd:], kv, EPI_BIAS_BF16)
+                out.append(kv)
+        return out
+
+    def forward(self, x, t, label=None, condition=None):
+        """x [B, z_scale, z_dim] f32, t [B] -> predicted noise [B, z_scale, z_dim] (score.py:117-151)."""
+        if not x.is_cuda:
+            raise RuntimeError("ldt_b200.Score.forward: CUDA tensors required (no CPU fallback)")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise RuntimeError("ldt_b200.Score is an inference path (sampling runs under torch.no_grad(), "
+                               "diffusion_continuous.py:232); call .eval() / use torch.no_grad()")
+        B = x.shape[0]
+        P = self.packed()
+        extra = None
+        kv_cond = None
+        if label is not None:
+            extra = self.LabelEmbedding(label).float().contiguous()
+        if condition is not None:
+            if isinstance(condition, dict):
+                raise NotImplementedError("ConditionNet prologue not built; pass (pts_cond, img_cond)")
+            cond_tokens, cond_vec = condition
+            if label is None and torch.is_tensor(cond_vec):
+                extra = cond_vec.float().contiguous()  # c = t_emb + condition[1]  (score.py:135)
+            if cond_tokens is not None:
+                kv_cond = self.project_condition_tokens(P, cond_tokens)
+        ws = self._workspace(B, B, x.device)
+        with torch.no_grad():
+            tt = t.to(device=x.device, dtype=torch.float32).contiguous()
+            mod = self.modulation(P, ws, tt, extra)
+            out = torch.empty((B, self.z_scale, self.z_dim), dtype=torch.float32, device=x.device)
+            xt = x.detach().float().contiguous().view(B * self.z_scale, self.z_dim)
+            self.run_tokens(P, ws, xt, mod, ws.mod_len, out.view(B * self.z_scale, self.z_dim), kv_cond)
+        return out
+
+
+class _PtrView:
+    """A raw device address passed where ops expects something with .data_ptr() (a column slice of a buffer)."""
+
+    __slots__ = ("_p",)
+
+    def __init__(self, p):
+        self._p = p
+
+    def data_ptr(self):
+        return self._p

@@ -1,0 +1,139 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/ldt_b200.h declares; the host mirrors keep
+the reference's state_dict layout; host-side logic (config validation, torch-RNG launch geometry, sharding)."""
+import ctypes as C
+import json
+import os
+import re
+
+import pytest
+import torch
+
+from tests.helpers import GOLDEN, airplane_config, ns
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "ldt_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ldt_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ldt_b200 import _lib
+    from ldt_b200.build import build
+    build()
+    lib = C.CDLL(_lib.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 12
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/ldt_b200.h but not exported"
+    # and the ctypes prototypes cover exactly the declared entry points
+    assert sorted(_lib.PROTOTYPES) == syms
+    L = _lib.load()
+    assert L.ldt_abi_version() == 1
+    assert isinstance(L.ldt_last_error_string(), bytes)
+
+
+def test_argument_validation_without_gpu():
+    """Entry points validate shapes before touching the device: error codes + messages, no CUDA call needed."""
+    from ldt_b200 import _lib
+    L = _lib.load()
+    assert L.ldt_nn_distance(-1, 4, None, 4, None, None, None, None, None, None) == -1
+    assert b"negative" in L.ldt_last_error_string()
+    assert L.ldt_nn_distance(0, 4, None, 4, None, None, None, None, None, None) == 0  # empty batch is a no-op
+    assert L.ldt_nn_distance(2, 4, None, 0, None, None, None, None, None, None) == -1  # one empty set: refuse
+    assert L.ldt_pairwise_cd(4, 4, 8, 8, None, None, 3, 2, None, None) == -1
+    assert L.ldt_pairwise_cd(4, 4, 8, 8, None, None, 2, 2, None, None) == 0  # empty row range
+    a = _lib.GemmArgs(M=128, N=128, K=100)
+    assert L.ldt_gemm_bf16(C.byref(a), None) == -1 and b"multiple of 64" in L.ldt_last_error_string()
+    assert L.ldt_attention_nk32(1, 4, 32, 48, None, 0, None, None, 0, None, None) == -3
+    assert L.ldt_layernorm_mod_bf16(4, 100, None, None, None, 0, 1, None, None, 1e-6, None, None) == -1
+    assert L.ldt_sde_step(9, 16, 1, 1, None, 1, None, 0, 0, 0, 0, 1, None, None) == -1
+
+
+def test_state_dict_layout_matches_reference():
+    """Keys, shapes AND order equal the reference modules' (checkpoint contract)."""
+    from ldt_b200 import Compressor, Score
+    lay = json.load(open(os.path.join(GOLDEN, "state_dict_layout.json")))
+    cfg = ns(airplane_config())
+    cfg.score.num_blocks = 2
+    mine = [[k, list(v.shape)] for k, v in Score(cfg.score).state_dict().items()]
+    assert mine == lay["score_2blocks"]
+    mine = [[k, list(v.shape)] for k, v in Compressor(cfg.compressor).state_dict().items()]
+    assert mine == lay["compressor"]
+    c = Compressor(cfg.compressor)
+    assert float(c.conv_in.initialized) == 0.0
+    c.init()
+    assert float(c.conv_in.initialized) == 1.0
+
+
+def test_config_validation_mirrors_reference_errors():
+    from ldt_b200 import Compressor, DiffusionVPSDE, Score
+    cfg = ns(airplane_config())
+    del cfg.score.condition  # the reference raises AttributeError on missing keys (score.py:56)
+    with pytest.raises(AttributeError):
+        Score(cfg.score)
+    cfg = ns(airplane_config())
+    cfg.score.unet = True
+    with pytest.raises(NotImplementedError):
+        Score(cfg.score)
+    sde = DiffusionVPSDE(cfg.sde, device="cpu")
+    assert sde.betas.dtype == torch.float32 and sde.betas.shape == (1000,)
+    with pytest.raises(NotImplementedError, match="preditor not Implemented"):  # message of diffusion_continuous.py:327
+        sde.sample_discrete(None, 1, 10, "nope", None, 1, (32, 120), 1e-6, False, True, 0.01, "cpu")
+    with pytest.raises(NotImplementedError, match="corrector not Implemented"):
+        sde.sample_discrete(None, 1, 10, "ancestral", "nope", 1, (32, 120), 1e-6, False, True, 0.01, "cpu")
+    with pytest.raises(NotImplementedError):
+        Compressor(cfg.compressor).forward(torch.zeros(1, 8, 3))
+
+
+def test_product_path_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under ldt_b200/ may import or reference it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "ldt_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("oracle/_ref", "").lower() or f == "nn_distance.cu", (dirpath, f)
+
+
+def test_cpu_tensors_fail_loudly():
+    from ldt_b200 import Score, ops
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.nn_distance_idx(torch.zeros(1, 4, 3), torch.zeros(1, 4, 3))
+    cfg = ns(airplane_config())
+    cfg.score.num_blocks = 1
+    cfg.score.hidden_size, cfg.score.num_heads, cfg.score.t_dim = 128, 2, 128
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Score(cfg.score).eval()(torch.zeros(1, 32, 120), torch.zeros(1))
+
+
+def test_sde_coefficient_table_matches_oracle_on_cpu():
+    """step_coefficients reproduces the per-step scalars of every predictor (bit-exact vs the oracle's op sequence)."""
+    from ldt_b200 import DiffusionVPSDE
+    from oracle import ldt_oracle as O
+    c = airplane_config()["sde"]
+    sde = DiffusionVPSDE(ns(airplane_config()).sde, device="cpu")
+    osde = O.VPSDE(c["beta_start"], c["beta_end"], c["sigma2_0"], c["sample_N"])
+    coef, ts = sde.step_coefficients("ancestral", 1000, 1e-6, False, torch.device("cpu"))
+    idx = (ts * 999).long()
+    assert torch.equal(coef[:, 0], torch.sqrt(osde.var(ts)))
+    assert torch.equal(coef[:, 1], osde.betas[idx])
+    assert torch.equal(coef[:, 2], torch.sqrt(1.0 - osde.betas[idx]))
+    assert torch.equal(coef[:, 3], torch.sqrt(osde.betas[idx]))
+    coef, ts = sde.step_coefficients("ddim", 1000, 1e-6, False, torch.device("cpu"))
+    assert float(coef[-1, 1]) == 1.0 and float(coef[-1, 4]) == 0.0  # last step: at_next = 1 (:169-170)
+    assert torch.equal(coef[:-1, 1], osde.alphas_cump[idx[:-1] - 1].sqrt())
+    raw, _ = sde.step_coefficients("eulermaruyama", 10, 1e-6, True, torch.device("cpu"), raw_score=True)
+    assert torch.all(raw[:, 0] == -1.0) and torch.all(raw[:, 4] == 0.0)
+
+
+def test_shard_ranges_cover_exactly():
+    from ldt_b200.distributed import shard_range
+    for total in (0, 1, 7, 2048, 2049):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,208 @@
+"""CPU suite (-m "not gpu"): pins the oracle to the reference.
+
+Every check compares ``oracle/`` against golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py) or against the reference's own known-answer criterion for the NN kernel
+(evaluation/ChamferDistancePytorch/unit_test.py:22-33: dist MSE < 1e-8 and index equality vs a float64 brute force).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ldt_oracle as O
+from tests.helpers import airplane_config, golden, ns, rel_rms_err, small_score_cfg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------------------------------------
+def _score_shapes(cfg):
+    H, T = cfg.hidden_size, cfg.t_dim
+    s = {}
+    for i in range(cfg.num_blocks):
+        p = f"Transformer.{i}."
+        s.update({p + "fc_q.weight": (H, H, 1), p + "fc_q.bias": (H,), p + "fc_kv.weight": (2 * H, H, 1),
+                  p + "fc_kv.bias": (2 * H,), p + "fc_o.weight": (H, H, 1), p + "fc_o.bias": (H,),
+                  p + "adaLN.1.weight": (6 * H, T), p + "adaLN.1.bias": (6 * H,),
+                  p + "mlp.fc.0.0.weight": (4 * H, H, 1), p + "mlp.fc.0.0.bias": (4 * H,),
+                  p + "mlp.out.weight": (H, 4 * H, 1), p + "mlp.out.bias": (H,)})
+    s.update({"ln_in.weight": (H, cfg.z_dim, 1), "ln_in.bias": (H,),
+              "TimeEmbedding.mlp.0.weight": (T, T // 4), "TimeEmbedding.mlp.0.bias": (T,),
+              "TimeEmbedding.mlp.2.weight": (T, T), "TimeEmbedding.mlp.2.bias": (T,),
+              "ln_out.adaLN.1.weight": (2 * H, T), "ln_out.adaLN.1.bias": (2 * H,),
+              "ln_out.ln.weight": (cfg.z_dim, H, 1), "ln_out.ln.bias": (cfg.z_dim,)})
+    return s
+
+
+def test_score_oracle_small_matches_reference():
+    cfg = small_score_cfg()
+    g = golden("score_small.npz")
+    sd = O.synth_state_dict(_score_shapes(cfg), 11)
+    out, blocks = O.score_forward(sd, cfg, g["x"], g["t"], return_blocks=True)
+    assert rel_rms_err(O.time_embedding(sd, g["t"]), g["c"]) < 1e-5
+    assert rel_rms_err(blocks[0].transpose(1, 2), g["h_block0"]) < 1e-5
+    assert rel_rms_err(out, g["params"]) < 1e-5
+
+
+def test_score_oracle_small_conditional_matches_reference():
+    cfg = small_score_cfg()
+    g = golden("score_small_cond.npz")
+    sd = O.synth_state_dict(_score_shapes(cfg), 11)
+    out = O.score_forward(sd, cfg, g["x"], g["t"], cond_tokens=g["pts_cond"], cond_vec=g["img_cond"])
+    assert rel_rms_err(out, g["params"]) < 1e-5
+
+
+def test_score_oracle_full_config_matches_reference():
+    cfg = ns(airplane_config()).score
+    g = golden("score_full.npz")
+    sd = O.synth_state_dict(_score_shapes(cfg), 12)
+    out = O.score_forward(sd, cfg, g["x"], g["t"])
+    assert rel_rms_err(out, g["params"]) < 2e-5
+
+
+def test_attention_layout_quirk_is_not_standard_mha():
+    """The reshape at model/layers.py:197 differs from textbook MHA; the oracle must implement the quirk."""
+    torch.manual_seed(0)
+    C_, H, N = 128, 2, 32
+    sd = O.synth_state_dict({"fc_q.weight": (C_, C_, 1), "fc_q.bias": (C_,), "fc_kv.weight": (2 * C_, C_, 1),
+                             "fc_kv.bias": (2 * C_,), "fc_o.weight": (C_, C_, 1), "fc_o.bias": (C_,)}, 3)
+    x = torch.randn(2, C_, N)
+    got = O.attention(sd, "", x, None, H)
+    q = O.conv1x1(x, sd["fc_q.weight"], sd["fc_q.bias"])
+    kv = O.conv1x1(x, sd["fc_kv.weight"], sd["fc_kv.bias"])
+    dh = C_ // H
+    qh = q.view(2, H, dh, N).transpose(2, 3)
+    kh = kv[:, :C_].reshape(2, H, dh, N).transpose(2, 3)
+    vh = kv[:, C_:].reshape(2, H, dh, N).transpose(2, 3)
+    w = ((qh @ kh.transpose(-1, -2)) * dh ** -0.5).softmax(-1)
+    std = (w @ vh).permute(0, 1, 3, 2).reshape(2, C_, N)  # textbook: heads back to channels
+    std = O.conv1x1(std, sd["fc_o.weight"], sd["fc_o.bias"])
+    assert (got - std).abs().max() > 1e-2
+    # and the closed form of the quirk: out[b, n', c'] = O[b,h,n,d], f=(h*N+n)*dh+d, n'=f//C, c'=f%C
+    o = (w @ vh)
+    flat = o.reshape(2, -1)
+    manual = flat.view(2, N, C_).transpose(1, 2)
+    assert torch.equal(O.conv1x1(manual, sd["fc_o.weight"], sd["fc_o.bias"]), got)
+
+
+# ------------------------------------------------------------------------------------------------
+def _compressor_decoder_shapes(cfg):
+    from ldt_b200.compressor import compressor_param_spec
+    return {k: v[0] for k, v in compressor_param_spec(cfg).items()}
+
+
+def test_decoder_oracle_matches_reference():
+    cfg = ns(airplane_config()).compressor
+    g = golden("decoder_full.npz")
+    sd = O.synth_state_dict(_compressor_decoder_shapes(cfg), 13)
+    torch.manual_seed(5)
+    full = O.decoder_sample(sd, cfg, g["eps"], 2048)
+    assert rel_rms_err(full, g["points_2048"]) < 2e-5
+    torch.manual_seed(5)
+    part = O.decoder_sample(sd, cfg, g["eps"], 1000)  # ragged: random 1000-row subset of the prior (ops.py:6-14)
+    assert part.shape == (2, 1000, 3)
+    assert rel_rms_err(part, g["points_1000"]) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------
+def test_sde_tables_match_reference():
+    g = golden("sde.npz")
+    c = airplane_config()["sde"]
+    sde = O.VPSDE(c["beta_start"], c["beta_end"], c["sigma2_0"], c["sample_N"])
+    assert torch.equal(sde.betas, g["betas"])
+    assert torch.equal(sde.alphas_cump, g["alphas_cump"])
+    assert float(sde.betas[0]) == pytest.approx(1e-4) and float(sde.betas[-1]) == pytest.approx(0.02)
+    ts = torch.linspace(1.0, 1e-6, 1000)
+    assert torch.equal(ts, g["timesteps"])
+    assert torch.equal(sde.var(ts), g["var"])
+    assert torch.equal(sde.g2(ts), g["g2"])
+    assert torch.equal(sde.e2int_f(ts), g["e2int_f"])
+    # idx = (t*(N-1)).long() walks 999..0 exactly
+    assert torch.equal((ts * 999).long(), torch.arange(999, -1, -1))
+
+
+@pytest.mark.parametrize("pred", ["ancestral", "reversediffusion", "eulermaruyama", "ddim"])
+def test_sde_predictors_match_reference_sampler(pred):
+    g = golden("sde.npz")
+    c = airplane_config()["sde"]
+    # the reference indexes its sample_N=1000 beta table with idx=(t*(N-1)).long() even when called with N=6
+    sde = O.VPSDE(c["beta_start"], c["beta_end"], c["sigma2_0"], c["sample_N"])
+
+    def net(x, t):
+        return 0.3 * x + torch.sin(5.0 * t)[:, None, None]
+
+    for key, denoise in (("mean", True), ("x", False)):
+        out = O.sample_discrete(sde, net, g[f"{pred}_x0"], 6, 1e-6, g[f"{pred}_noise"], predictor=pred, denoise=denoise)
+        assert torch.equal(out, g[f"{pred}_{key}"]), f"{pred}/{key}: max diff {(out - g[f'{pred}_{key}']).abs().max()}"
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def oracle_nn():
+    lib = os.path.join(ROOT, "oracle", "liboracle_nn.so")
+    if not os.path.exists(lib):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle_nn.so"])
+    L = C.CDLL(lib)
+    L.oracle_nn_distance.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_void_p] * 4
+    L.oracle_pairwise_cd.argtypes = [C.c_int] * 4 + [C.c_void_p] * 2 + [C.c_int] * 2 + [C.c_void_p, C.c_int]
+    return L
+
+
+def c_nn_distance(L, a, b):
+    a, b = a.contiguous().float(), b.contiguous().float()
+    bs, n, m = a.shape[0], a.shape[1], b.shape[1]
+    d1, d2 = torch.empty(bs, n), torch.empty(bs, m)
+    i1, i2 = torch.empty(bs, n, dtype=torch.int32), torch.empty(bs, m, dtype=torch.int32)
+    L.oracle_nn_distance(bs, n, a.data_ptr(), m, b.data_ptr(), d1.data_ptr(), i1.data_ptr(), d2.data_ptr(), i2.data_ptr())
+    return d1, i1, d2, i2
+
+
+def test_nn_oracle_meets_reference_unit_test_criterion(oracle_nn):
+    """unit_test.py:22-33: mean sq. error of distances < 1e-8 and index difference norm == 0."""
+    g = golden("nn.npz")
+    d1, i1, d2, i2 = c_nn_distance(oracle_nn, g["p1"], g["p2"])
+    assert float(((d1 - g["dist1"]) ** 2).mean() + ((d2 - g["dist2"]) ** 2).mean()) < 1e-8
+    assert torch.equal(i1, g["idx1"]) and torch.equal(i2, g["idx2"])
+
+
+def test_nn_oracle_ties_lowest_index_and_ragged(oracle_nn):
+    g = golden("nn.npz")
+    d1, i1, d2, i2 = c_nn_distance(oracle_nn, g["q1"], g["q2"])
+    assert float(((d1 - g["qdist1"]) ** 2).mean() + ((d2 - g["qdist2"]) ** 2).mean()) < 1e-8
+    # q2 = [q1[:5], random, q1[:5]]: the first five query points have two exact matches; strict `<` keeps the lower
+    assert torch.equal(i1[:, :5], torch.arange(5, dtype=torch.int32).expand(2, 5))
+    assert torch.all(d1[:, :5] == 0)
+    # single-point sets
+    a, b = torch.rand(3, 1, 3), torch.rand(3, 7, 3)
+    e1, j1, e2, j2 = c_nn_distance(oracle_nn, a, b)
+    assert torch.all(j2 == 0) and e1.shape == (3, 1)
+    f = O.nn_distance_f64(a, b)
+    assert torch.equal(j1.long(), f[1])
+
+
+def test_pairwise_cd_and_metrics_match_reference(oracle_nn):
+    g = golden("metrics.npz")
+    ref, smp = g["ref"], g["smp"]
+
+    def cd(a, b):
+        out = torch.empty(a.shape[0], b.shape[0])
+        oracle_nn.oracle_pairwise_cd(a.shape[0], b.shape[0], a.shape[1], b.shape[1], a.contiguous().data_ptr(),
+                                     b.contiguous().data_ptr(), 0, a.shape[0], out.data_ptr(), 2)
+        return out
+
+    M_rs, M_rr, M_ss = cd(ref, smp), cd(ref, ref), cd(smp, smp)
+    # the reference ran its bmm fallback here (|x|^2+|y|^2-2xy, evaluation_metrics.py:23-33): few-ulp differences
+    for mine, theirs in ((M_rs, g["M_rs"]), (M_rr, g["M_rr"]), (M_ss, g["M_ss"])):
+        assert torch.allclose(mine, theirs, rtol=1e-4, atol=1e-6)
+    mc = O.lgan_mmd_cov(M_rs.t())
+    assert float(mc["mmd"]) == pytest.approx(float(g["mmd"]), rel=1e-4)
+    assert float(mc["cov"]) == float(g["cov"])
+    kn = O.knn_1nna(M_rr, M_rs, M_ss, 1)
+    for k in ("acc", "tp", "fp", "fn", "tn"):
+        assert float(kn[k]) == float(g[k])
+    # python-level restatement through nn_fn agrees with the C one
+    M2 = O.pairwise_cd(ref, smp, lambda a, b: (lambda r: (r[0], r[2]))(c_nn_distance(oracle_nn, a, b)))
+    assert torch.allclose(M2, M_rs, rtol=1e-6, atol=0)
