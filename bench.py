@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the LDT sampling hot path on B200 (driver contract: one JSON line on stdout from rank 0).
+
+One "step" = one full pass of the hot path over one batch: the reverse-SDE loop (sample_N = 1000 ancestral steps
+of the 24-block score net, experiments/Latent_Diffusion_Trainer config) followed by the Compressor decode to 2048
+points, for 256 point clouds per GPU (BASELINE.json configs[1]; weak scaling over GPUs, one process per GPU, the
+only collective is the final all-gather of generated points).
+
+  value      clouds/s, whole job, latents already in HBM when the timed region starts
+  e2e        the same through the reference-facing API (DiffusionVPSDE.sample_discrete + Compressor.sample, i.e.
+             what Trainer.sample calls) with host buffers: CPU-generator x0 -> H2D inside, points D2H inside
+  roofline   the dense-contraction kernel (tcgen05 GEMM): algorithmic FLOPs / CUDA-event kernel time, vs the
+             measured cuBLAS bf16 peak in MEASURED_PEAKS.json
+  cd         secondary metric of BASELINE.json: Chamfer cloud-pairs/s (2048-point clouds)
+  cpu_baseline / --impl reference: the oracle port of the reference's CPU path on the host cores (bounded sample)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from tests.helpers import airplane_config, ns  # noqa: E402  (shipped experiment configuration values)
+
+FLOP_SCORE_PER_SAMPLE_STEP = 19.44e9  # unconditional token path, per sample per SDE step
+FLOP_DECODE_PER_CLOUD = 4.24e9
+METRIC = "point clouds/sec full SDE sample+decode @2048 pts"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="clouds per GPU per step")
+    ap.add_argument("--sde-steps", type=int, default=1000, help="reverse-SDE steps (config: 1000)")
+    ap.add_argument("--points", type=int, default=2048)
+    ap.add_argument("--cd-clouds", type=int, default=192, help="clouds per set for the Chamfer-matrix metric")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), float(p["bf16_tflops"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 1400.0, 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        fd, self.path = tempfile.mkstemp(suffix=".csv")
+        os.close(fd)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        rows = []
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                try:
+                    rows.append((float(parts[0]), float(parts[1]), float(parts[2]), parts[3:7]))
+                except ValueError:
+                    pass
+        os.unlink(self.path)
+        if rows:
+            sm = sorted(r[0] for r in rows)
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["sm_max_mhz"] = rows[0][1]
+            out["power_w_max"] = max(r[2] for r in rows)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            out["reasons"] = [n for i, n in enumerate(names) if any(r[3][i].lower().startswith("active") for r in rows)]
+            out["samples"] = len(rows)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm: the oracle port of the reference path on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(batch, sde_steps_total, points, sample_steps, threads):
+    """Time a BOUNDED sample of the workload on CPU: `sample_steps` score evaluations + predictor updates at batch
+    `batch`, plus one decode, and extrapolate to the full step count (every step costs the same).  Returns clouds/s."""
+    from oracle import ldt_oracle as O
+    torch.set_num_threads(threads)
+    c = ns(airplane_config())
+    torch.manual_seed(0)
+    from ldt_b200.compressor import compressor_param_spec
+    from tests.test_oracle_golden import _score_shapes
+    sd = O.synth_state_dict(_score_shapes(c.score), 12)
+    csd = O.synth_state_dict({k: v[0] for k, v in compressor_param_spec(c.compressor).items()}, 13)
+    sde = O.VPSDE(c.sde.beta_start, c.sde.beta_end, c.sde.sigma2_0, c.sde.sample_N)
+    x = torch.randn(batch, 32, 120)
+    ts = torch.linspace(1.0, 1e-6, sde_steps_total)
+    with torch.no_grad():
+        O.score_forward(sd, c.score, x, torch.ones(batch) * ts[0])  # warm-up
+        t0 = time.perf_counter()
+        for i in range(sample_steps):
+            vt = torch.ones(batch) * ts[i]
+            prm = O.score_forward(sd, c.score, x, vt)
+            x, xm = O.ancestral_step(sde, x, vt, prm, torch.randn_like(x), sde_steps_total)
+        t_step = (time.perf_counter() - t0) / sample_steps
+        t0 = time.perf_counter()
+        O.decoder_sample(csd, c.compressor, xm, points)
+        t_dec = time.perf_counter() - t0
+    total = sde_steps_total * t_step + t_dec
+    return batch / total, t_step, t_dec
+
+
+def cpu_cd_pairs_per_s(threads, n=8, pts=2048):
+    import ctypes as C
+    lib = os.path.join(ROOT, "oracle", "liboracle_nn.so")
+    if not os.path.exists(lib):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle_nn.so"], stdout=subprocess.DEVNULL)
+    L = C.CDLL(lib)
+    L.oracle_pairwise_cd.argtypes = [C.c_int] * 4 + [C.c_void_p] * 2 + [C.c_int] * 2 + [C.c_void_p, C.c_int]
+    a, b = torch.randn(n, pts, 3), torch.randn(n, pts, 3)
+    out = torch.empty(n, n)
+    t0 = time.perf_counter()
+    L.oracle_pairwise_cd(n, n, pts, pts, a.data_ptr(), b.data_ptr(), 0, n, out.data_ptr(), threads)
+    return n * n / (time.perf_counter() - t0)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    batch = 16  # BASELINE.json configs[0]: the reference's own CPU-runnable case
+    vals = []
+    t_all = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        v, t_step, t_dec = cpu_reference_sample(batch, args.sde_steps, args.points, args.cpu_sample_steps, threads)
+        if i >= args.warmup:
+            vals.append(v)
+        if time.perf_counter() - t_all > 240:  # stay within a few minutes
+            if not vals:
+                vals.append(v)
+            break
+    value = sum(vals) / len(vals)
+    sample = (f"batch {batch}: {args.cpu_sample_steps} score-net evaluations + ancestral updates and 1 decode timed, "
+              f"extrapolated linearly to {args.sde_steps} steps (t_step={t_step:.3f}s, t_decode={t_dec:.3f}s)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": args.gpus,
+        "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * batch / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init weights, N(0,1) latents)",
+        "config": {"workload": f"unconditional sampling, {args.sde_steps} ancestral SDE steps + decode, {args.points} pts, "
+                               f"CPU oracle port of the reference path (torch fp32, {threads} threads)"},
+        "cpu_baseline": {"value": value, "unit": "clouds/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    assert torch.cuda.is_available(), "bench.py needs a GPU for --impl ours (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    from ldt_b200 import Compressor, DiffusionVPSDE, Score, ops
+    from ldt_b200.sampler import fused_sample_loop
+
+    c = ns(airplane_config())
+    torch.manual_seed(0)  # common_init(seed=0): random-init weights (BASELINE.json configs)
+    model = Score(c.score).to(dev).eval()
+    comp = Compressor(c.compressor).to(dev).eval()
+    sde = DiffusionVPSDE(c.sde, device=dev)
+    B, N, P = args.batch, args.sde_steps, args.points
+
+    class Trainer:  # the slice of trainer/Latent_SDE_Trainer.py that sampling uses (:57-61, :143-165)
+        def __init__(self):
+            self.model, self.SDE = model, sde
+
+        def score_fn(self, t, x, label=None, condition=None):
+            t = t.to(x)
+            params = self.model(x, t, label=label, condition=condition)
+            return -params / torch.sqrt(self.SDE.var(t))[:, None, None], params
+
+        def sample(self, num_samples):
+            eps = self.SDE.sample_discrete(score_fn=self.score_fn, N=N, corrector=c.sde.corrector, predictor=c.sde.predictor,
+                                           corrector_steps=c.sde.corrector_steps, shape=(c.score.z_scale, c.score.z_dim),
+                                           time_eps=c.sde.sample_time_eps, label=None, denoise=c.sde.denoise, device=dev,
+                                           num_samples=num_samples, probability_flow=c.sde.probability_flow, snr=c.sde.snr,
+                                           condition=None)
+            return comp.sample((num_samples, P), given_eps=eps), eps
+
+    tr = Trainer()
+    torch.manual_seed(1234 + rank)
+    torch.cuda.manual_seed(1234 + rank)
+    x0 = torch.randn(B, c.score.z_scale, c.score.z_dim).to(dev)
+
+    def device_step():
+        eps = fused_sample_loop(model, sde, x0, N, c.sde.predictor, c.sde.sample_time_eps, c.sde.probability_flow, c.sde.denoise)
+        pts = comp.sample((B, P), given_eps=eps)
+        if world > 1:
+            out = [torch.empty_like(pts) for _ in range(world)]
+            dist.all_gather(out, pts)
+        return pts
+
+    host_pts = torch.empty((B, P, 3), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        pts, _ = tr.sample(B)  # CPU-generator x0 + H2D inside (diffusion_continuous.py:237)
+        if world > 1:
+            out = [torch.empty_like(pts) for _ in range(world)]
+            dist.all_gather(out, pts)
+        host_pts.copy_(pts, non_blocking=False)  # D2H of the generated clouds (valsample np.save, :207-210)
+        return host_pts
+
+    launches_before = ops.launch_count()
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        device_step()
+    ev1.record()
+    barrier()
+    t_dev = ev0.elapsed_time(ev1) / 1e3
+    gpu_launches = ops.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else {}
+
+    # end-to-end arm through the public API, host buffers in and out
+    e2e_step()
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    ev1.record()
+    barrier()
+    t_e2e = ev0.elapsed_time(ev1) / 1e3
+
+    tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e = float(tt[0]), float(tt[1])
+
+    # ---- roofline of the dominant kernel: eager pass over one SDE step with CUDA events around every GEMM ----
+    roof = None
+    cd = None
+    if rank == 0:
+        sus, burst, hbm, src = peaks()
+        from ldt_b200 import profiling
+        prof = profiling.profile_score_step(model, B)
+        gemm_ms, gemm_flop = prof["gemm_ms"], prof["gemm_flop"]
+        achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12
+        step_flop = B * (N * FLOP_SCORE_PER_SAMPLE_STEP + FLOP_DECODE_PER_CLOUD)
+        roof = {"bound": "tensor", "achieved": achieved, "peak": sus, "unit": "TFLOP/s", "frac": achieved / sus, "traffic": None,
+                "kernel": "gemm_tc_kernel (tcgen05.mma, TMEM accumulators, TMA-fed)", "peak_source": src + ", sustained figure",
+                "launches_timed": prof["gemm_launches"], "gemm_share_of_step": prof["gemm_ms"] / prof["total_ms"],
+                "whole_step_achieved": step_flop * args.steps / t_dev / 1e12,
+                "whole_step_frac": step_flop * args.steps / t_dev / 1e12 / sus,
+                "per_kernel_ms": prof["by_kind"]}
+        # ---- secondary metric: Chamfer cloud-pairs/s ----
+        n = args.cd_clouds
+        g = torch.Generator().manual_seed(7)
+        a = torch.randn((n, P, 3), generator=g).to(dev)
+        b = torch.randn((n, P, 3), generator=g).to(dev)
+        ops.pairwise_cd(a, b)
+        torch.cuda.synchronize()
+        ev0.record()
+        reps = 3
+        for _ in range(reps):
+            ops.pairwise_cd(a, b)
+        ev1.record()
+        torch.cuda.synchronize()
+        t_cd = ev0.elapsed_time(ev1) / 1e3 / reps
+        pair_evals = n * n * P * P
+        cd = {"metric": "CD cloud-pairs/sec @2048x2048 pts", "value": n * n / t_cd, "unit": "pairs/s", "matrix": f"{n}x{n}",
+              "point_pair_evals_per_s": pair_evals / t_cd,
+              "roofline": {"bound": "fp32-issue", "achieved": pair_evals * 8 / t_cd / 1e12, "unit": "TFLOP/s (8 flop per point pair, each pair once)",
+                           "peak": 148 * 128 * 2 * 1.965e9 / 1e12, "peak_source": "nominal: 148 SMs x 128 FP32 lanes x 2 x 1.965 GHz",
+                           "frac": pair_evals * 8 / t_cd / (148 * 128 * 2 * 1.965e9)}}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, t_step, t_dec = cpu_reference_sample(16, N, P, args.cpu_sample_steps, threads)
+        cpu = {"value": v, "unit": "clouds/s", "cores": threads, "kind": "port",
+               "sample": f"oracle port of the reference path (torch fp32): batch 16, {args.cpu_sample_steps} score evaluations + 1 decode "
+                         f"timed, extrapolated to {N} steps (t_step={t_step:.3f}s, t_decode={t_dec:.3f}s)",
+               "cd_pairs_per_s": cpu_cd_pairs_per_s(threads)}
+
+    if rank == 0:
+        clouds = B * world * args.steps
+        line = {
+            "metric": METRIC, "value": clouds / t_dev, "unit": "clouds/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random-init weights seed 0, N(0,1) latents)",
+            "config": {"workload": f"BASELINE configs[1]: unconditional sampling, batch {B}/GPU, {N} ancestral reverse-SDE steps "
+                                   f"(24-block width-1024 score net) + Compressor decode to {P} pts",
+                       "batch_per_gpu": B, "sde_steps": N, "points": P, "parallelism": f"dp{world} (sample batch split, final all-gather)",
+                       "l2": "per-step working set (604 MB bf16 weights + activations) exceeds the 126 MB L2; no flush needed"},
+            "e2e": {"value": clouds / t_e2e, "unit": "clouds/s", "h2d_bytes_per_step": B * 32 * 120 * 4,
+                    "d2h_bytes_per_step": B * P * 3 * 4, "api": "DiffusionVPSDE.sample_discrete(score_fn=Trainer.score_fn) + Compressor.sample"},
+            "gpu_launches": gpu_launches, "roofline": roof, "cpu_baseline": cpu, "cd": cd, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

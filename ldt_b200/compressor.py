@@ -303,5 +303,6 @@ class Compressor(nn.Module):
 def _cast_strided(view, ld_in, cols, out):
     """cast_pad on a column slice of a row-major f32 matrix (rows = view.shape[0], leading dim ld_in)."""
     from ._lib import check, load, ptr, stream_ptr
-    check(load().ldt_cast_pad_bf16(view.shape[0], cols, view.data_ptr(), ld_in, ptr(out), out.shape[1], stream_ptr()),
-          "ldt_cast_pad_bf16")
+    with ops._launch("cast"):
+        check(load().ldt_cast_pad_bf16(view.shape[0], cols, view.data_ptr(), ld_in, ptr(out), out.shape[1], stream_ptr()),
+              "ldt_cast_pad_bf16")

@@ -13,6 +13,54 @@ from ._lib import (EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_GATE_RES
                    ptr, stream_ptr)
 
 
+# ---- launch accounting / optional per-launch CUDA-event profiling (bench.py roofline) ----------------------
+_LAUNCHES = [0]
+_PROFILE = None  # None, or a list receiving (kind, start_event, end_event, note)
+
+
+def launch_count() -> int:
+    """Number of ldt_b200 kernels launched so far by this process (graph replays included)."""
+    return _LAUNCHES[0]
+
+
+def add_launches(n: int) -> None:
+    _LAUNCHES[0] += n
+
+
+class profile:
+    """Context manager: record a CUDA-event pair around every kernel launch made through this module."""
+
+    def __enter__(self):
+        global _PROFILE
+        _PROFILE = []
+        return _PROFILE
+
+    def __exit__(self, *a):
+        global _PROFILE
+        _PROFILE = None
+
+
+class _launch:
+    __slots__ = ("kind", "n", "note", "ev")
+
+    def __init__(self, kind, n=1, note=None):
+        self.kind, self.n, self.note, self.ev = kind, n, note, None
+
+    def __enter__(self):
+        if _PROFILE is not None:
+            self.ev = torch.cuda.Event(enable_timing=True)
+            self.ev.record()
+        return self
+
+    def __exit__(self, et, ev, tb):
+        _LAUNCHES[0] += self.n
+        if _PROFILE is not None and et is None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            _PROFILE.append((self.kind, self.ev, e, self.note))
+        return False
+
+
 def _req(t: torch.Tensor, dtype, name: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor")
@@ -33,7 +81,7 @@ def nn_distance_idx(a: torch.Tensor, b: torch.Tensor):
     idx1 = torch.empty((bs, n), dtype=torch.int32, device=a.device)
     dist2 = torch.empty((bs, m), dtype=torch.float32, device=a.device)
     idx2 = torch.empty((bs, m), dtype=torch.int32, device=a.device)
-    with torch.cuda.device(a.device):
+    with torch.cuda.device(a.device), _launch("nn_distance", 2):
         check(load().ldt_nn_distance(bs, n, ptr(a), m, ptr(b), ptr(dist1), ptr(idx1), ptr(dist2), ptr(idx2),
                                      stream_ptr()), "ldt_nn_distance")
     return dist1, idx1, dist2, idx2
@@ -49,7 +97,7 @@ def pairwise_cd(a: torch.Tensor, b: torch.Tensor, row_begin: int = 0, row_end: i
     nb, pb = b.shape[0], b.shape[1]
     row_end = na if row_end is None else row_end
     out = torch.empty((row_end - row_begin, nb), dtype=torch.float32, device=a.device)
-    with torch.cuda.device(a.device):
+    with torch.cuda.device(a.device), _launch("pairwise_cd"):
         check(load().ldt_pairwise_cd(na, nb, pa, pb, ptr(a), ptr(b), row_begin, row_end, ptr(out), stream_ptr()),
               "ldt_pairwise_cd")
     return out
@@ -68,7 +116,7 @@ def gemm(A: torch.Tensor, W: torch.Tensor, bias, out: torch.Tensor, epilogue: in
     args = GemmArgs(M=M, N=N, K=K, A=ptr(A), lda=A.stride(0), W=ptr(W), ldw=W.stride(0), bias=ptr(bias),
                     out=ptr(out2), ldo=out2.stride(0), epilogue=epilogue, resid=ptr(resid), gate=ptr(gate),
                     gate_stride=gate_stride, rows_per_gate=rows_per_gate, backend=backend)
-    with torch.cuda.device(A.device):
+    with torch.cuda.device(A.device), _launch("gemm", 1, (M, N, K, epilogue)):
         check(load().ldt_gemm_bf16(C.byref(args), stream_ptr()), "ldt_gemm_bf16")
     return out
 
@@ -80,7 +128,7 @@ def cast_pad_bf16(x: torch.Tensor, ld_out: int, out: torch.Tensor | None = None)
     rows, cols = x2.shape
     if out is None:
         out = torch.empty((rows, ld_out), dtype=torch.bfloat16, device=x.device)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _launch("cast"):
         check(load().ldt_cast_pad_bf16(rows, cols, ptr(x2), x2.stride(0), ptr(out), ld_out, stream_ptr()),
               "ldt_cast_pad_bf16")
     return out
@@ -92,7 +140,7 @@ def pack_weight(w: torch.Tensor, ld_out: int | None = None) -> torch.Tensor:
     rows, cols = w2.shape
     ld_out = ((cols + 63) // 64) * 64 if ld_out is None else ld_out
     out = torch.empty((rows, ld_out), dtype=torch.bfloat16, device=w.device)
-    with torch.cuda.device(w.device):
+    with torch.cuda.device(w.device), _launch("pack"):
         check(load().ldt_pack_weights(rows, cols, ptr(w2), cols, ptr(out), ld_out, stream_ptr()), "ldt_pack_weights")
     return out
 
@@ -100,7 +148,7 @@ def pack_weight(w: torch.Tensor, ld_out: int | None = None) -> torch.Tensor:
 def layernorm_mod(x: torch.Tensor, out: torch.Tensor, *, shift=None, scale=None, mod_stride: int = 0,
                   rows_per_mod: int = 1, weight=None, bias=None, eps: float = 1e-6) -> torch.Tensor:
     rows, Cc = x.shape
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _launch("layernorm"):
         check(load().ldt_layernorm_mod_bf16(rows, Cc, ptr(x), ptr(shift), ptr(scale), mod_stride, rows_per_mod,
                                             ptr(weight), ptr(bias), eps, ptr(out), stream_ptr()),
               "ldt_layernorm_mod_bf16")
@@ -109,32 +157,32 @@ def layernorm_mod(x: torch.Tensor, out: torch.Tensor, *, shift=None, scale=None,
 
 def time_embedding(t, freq, w0, b0, w1, b1, extra, c_out, silu_out, scratch) -> None:
     R, half, D = t.shape[0], freq.shape[0], w1.shape[0]
-    with torch.cuda.device(t.device):
+    with torch.cuda.device(t.device), _launch("time_embedding", 3):
         check(load().ldt_time_embedding(R, half, D, ptr(t), ptr(freq), ptr(w0), ptr(b0), ptr(w1), ptr(b1), ptr(extra),
                                         ptr(c_out), ptr(silu_out), ptr(scratch), stream_ptr()), "ldt_time_embedding")
 
 
 def attention_nk32(B: int, H: int, Nq: int, dh: int, q, ldq: int, k, v, ldkv: int, o) -> None:
-    with torch.cuda.device(o.device):
+    with torch.cuda.device(o.device), _launch("attention"):
         check(load().ldt_attention_nk32(B, H, Nq, dh, ptr(q), ldq, ptr(k), ptr(v), ldkv, ptr(o), stream_ptr()),
               "ldt_attention_nk32")
 
 
 def sde_step(predictor: int, x, params, z, coef_table, step_index, seed: int, offset: int, offset_per_step: int,
              rng_grid: int, x_next, x_mean) -> None:
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _launch("sde_step"):
         check(load().ldt_sde_step(predictor, x.numel(), ptr(x), ptr(params), ptr(z), ptr(coef_table), ptr(step_index),
                                   seed, offset, offset_per_step, rng_grid, ptr(x_next), ptr(x_mean), stream_ptr()),
               "ldt_sde_step")
 
 
 def advance_step(step_index) -> None:
-    with torch.cuda.device(step_index.device):
+    with torch.cuda.device(step_index.device), _launch("advance_step"):
         check(load().ldt_advance_step(ptr(step_index), stream_ptr()), "ldt_advance_step")
 
 
 def select_row(table, step_index, out) -> None:
-    with torch.cuda.device(out.device):
+    with torch.cuda.device(out.device), _launch("select_row"):
         check(load().ldt_select_row(ptr(table), table.shape[1], ptr(step_index), ptr(out), stream_ptr()),
               "ldt_select_row")
 

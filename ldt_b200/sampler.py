@@ -103,12 +103,16 @@ class StepGraph:
             self.step.zero_()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
             with torch.cuda.graph(g):
                 self._step_body()
+            self.launches_per_step = ops.launch_count() - n0
+            ops.add_launches(-self.launches_per_step)  # captured, not executed
             self.graph = g
             # the capture itself does not execute; state is still (x0, step 0)
         for _ in range(self.N):
             self.graph.replay()
+        ops.add_launches(self.N * self.launches_per_step)
 
 
 _graph_cache: dict = {}

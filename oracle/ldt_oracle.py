@@ -24,13 +24,27 @@ import torch.nn.functional as F
 
 LN_EPS = 1e-6  # tools/utils.py:130
 
+# Optional operand-rounding hook.  With QUANT = None (default) this file is the plain fp32/fp64 restatement of the
+# reference.  Tests may set QUANT = bf16_round to emulate WHERE the B200 path rounds operands to bf16 (GEMM inputs,
+# stored q/k/v, softmax probabilities, MLP hidden) while keeping the reference's algorithm, to separate "bf16
+# operand noise" from "wrong algorithm" when comparing against the fp32 reference.
+QUANT = None
+
+
+def bf16_round(x):
+    return x.to(torch.bfloat16).to(x.dtype)
+
+
+def _q(x):
+    return x if QUANT is None else QUANT(x)
+
 
 # --------------------------------------------------------------------------------------------------
 # building blocks
 # --------------------------------------------------------------------------------------------------
 def conv1x1(x, w, b):
     """nn.Conv1d(kernel_size=1) on channels-first [B, C, N]; w is [out, in, 1]."""
-    return torch.einsum("oc,bcn->bon", w[:, :, 0], x) + b[None, :, None]
+    return torch.einsum("oc,bcn->bon", _q(w[:, :, 0]), _q(x)) + b[None, :, None]
 
 
 def layer_norm_cf(x, weight=None, bias=None):
@@ -60,8 +74,8 @@ def attention(sd, prefix, x, y, num_heads):
     """ResidualBlock.compute_attention, model/layers.py:183-200, including the head-layout quirk at :197."""
     if y is None:
         y = x
-    query = conv1x1(x, sd[prefix + "fc_q.weight"], sd[prefix + "fc_q.bias"])
-    kv = conv1x1(y, sd[prefix + "fc_kv.weight"], sd[prefix + "fc_kv.bias"])
+    query = _q(conv1x1(x, sd[prefix + "fc_q.weight"], sd[prefix + "fc_q.bias"]))
+    kv = _q(conv1x1(y, sd[prefix + "fc_kv.weight"], sd[prefix + "fc_kv.bias"]))
     B, Cc, N = query.shape
     key, value = kv[:, :Cc, :], kv[:, Cc:, :]
     M = key.shape[2]
@@ -71,6 +85,10 @@ def attention(sd, prefix, x, y, num_heads):
     v = value.reshape(B, num_heads, dh, M).permute(0, 1, 3, 2)
     w = (q @ k.transpose(-2, -1)) * (dh ** -0.5)
     w = w.softmax(dim=-1)
+    if QUANT is not None:  # the kernel rounds un-normalised probabilities exp(s - max) and divides afterwards
+        sc_ = (q @ k.transpose(-2, -1)) * (dh ** -0.5)
+        e = torch.exp(sc_ - sc_.amax(-1, keepdim=True))
+        w = _q(e) / e.sum(-1, keepdim=True)
     att = (w @ v).reshape(B, N, Cc).transpose(1, 2)  # :197 -- heads are NOT permuted back
     return conv1x1(att, sd[prefix + "fc_o.weight"], sd[prefix + "fc_o.bias"])
 
@@ -84,7 +102,7 @@ def mlp(sd, prefix, x):
 def residual_block_adaln(sd, prefix, x, y, c, num_heads):
     """ResidualBlock.forward, AdaLN branch with dim_in == dim_out: model/layers.py:211-219."""
     cc = c[:, None, :] if c.dim() == 2 else c.transpose(1, 2)
-    mod = F.linear(F.silu(cc), sd[prefix + "adaLN.1.weight"], sd[prefix + "adaLN.1.bias"]).transpose(1, 2)
+    mod = F.linear(_q(F.silu(cc)), _q(sd[prefix + "adaLN.1.weight"]), sd[prefix + "adaLN.1.bias"]).transpose(1, 2)
     shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = mod.chunk(6, dim=1)
     h = layer_norm_cf(x) * (1 + scale_msa) + shift_msa
     x = x + gate_msa * attention(sd, prefix, h, y, num_heads)
@@ -120,7 +138,7 @@ def score_forward(sd, cfg, x, t, cond_tokens=None, cond_vec=None, return_blocks=
         if return_blocks:
             blocks.append(h)
     # FinalLayer, model/layers.py:240-245
-    mod = F.linear(F.silu(c[:, None, :]), sd["ln_out.adaLN.1.weight"], sd["ln_out.adaLN.1.bias"]).transpose(1, 2)
+    mod = F.linear(_q(F.silu(c[:, None, :])), _q(sd["ln_out.adaLN.1.weight"]), sd["ln_out.adaLN.1.bias"]).transpose(1, 2)
     shift, scale = mod.chunk(2, dim=1)
     h = layer_norm_cf(h) * (1 + scale) + shift
     out = conv1x1(h, sd["ln_out.ln.weight"], sd["ln_out.ln.bias"]).transpose(1, 2)

@@ -51,3 +51,19 @@ def rel_rms_err(a: torch.Tensor, b: torch.Tensor) -> float:
 
 def shapes_of(module) -> dict:
     return {k: tuple(v.shape) for k, v in module.state_dict().items()}
+
+
+def rms_rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    """rms(a-b) / rms(b)."""
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt().clamp_min(1e-30))
+
+
+def assert_bf16_close(got: torch.Tensor, ref: torch.Tensor, extra_rel: float = 0.0, what: str = "") -> None:
+    """Element-wise bound for a value that was rounded once to bf16: half an ulp is 2^-9 relative; allow 2^-8 plus
+    `extra_rel` of the tensor's rms for fp32 accumulation-order differences upstream of the rounding."""
+    got, ref = got.double().cpu(), ref.double().cpu()
+    rms = ref.pow(2).mean().sqrt()
+    bound = ref.abs() * 2.0 ** -8 + (extra_rel + 1e-6) * rms
+    bad = (got - ref).abs() > bound
+    assert not bad.any(), f"{what}: {int(bad.sum())} elements outside the bf16 bound, worst {(got - ref).abs().max():.3e}"

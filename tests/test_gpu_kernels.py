@@ -1,0 +1,357 @@
+"""GPU parity tests for the individual sm_100a kernels, all called through the C ABI (ldt_b200.ops -> ctypes).
+
+Checker = oracle/ (CPU restatement pinned to the reference) and, for the NN kernel, the reference's own CUDA kernel
+compiled into oracle/_ref/libref_nnd.so.  Bars: bit-exact for distances / indices / the SDE update given identical
+inputs; stated tolerances for bf16-input, fp32-accumulate contractions.
+"""
+import ctypes as C
+import os
+
+import pytest
+import torch
+
+from oracle import ldt_oracle as O
+from tests.helpers import airplane_config, assert_bf16_close, golden, ns, rel_rms_err, rms_rel_err
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests selected but no CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def oracle_nn():
+    L = C.CDLL(os.path.join(ROOT, "oracle", "liboracle_nn.so"))
+    L.oracle_nn_distance.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_void_p] * 4
+    L.oracle_pairwise_cd.argtypes = [C.c_int] * 4 + [C.c_void_p] * 2 + [C.c_int] * 2 + [C.c_void_p, C.c_int]
+    return L
+
+
+def cpu_nn(L, a, b):
+    a, b = a.cpu().contiguous(), b.cpu().contiguous()
+    bs, n, m = a.shape[0], a.shape[1], b.shape[1]
+    d1, d2 = torch.empty(bs, n), torch.empty(bs, m)
+    i1, i2 = torch.empty(bs, n, dtype=torch.int32), torch.empty(bs, m, dtype=torch.int32)
+    L.oracle_nn_distance(bs, n, a.data_ptr(), m, b.data_ptr(), d1.data_ptr(), i1.data_ptr(), d2.data_ptr(), i2.data_ptr())
+    return d1, i1, d2, i2
+
+
+# ------------------------------------------------------------------------------------------------
+# NN distance / Chamfer matrix
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bs,n,m", [(4, 100, 200), (3, 2048, 2048), (2, 1, 7), (1, 1025, 513), (5, 37, 2049)])
+def test_nn_distance_bit_exact_vs_oracle(dev, oracle_nn, bs, n, m):
+    from ldt_b200 import ops
+    g = torch.Generator().manual_seed(n * 7 + m)
+    a, b = torch.rand((bs, n, 3), generator=g), torch.rand((bs, m, 3), generator=g) * 1.3 - 0.1
+    d1, i1, d2, i2 = [t.cpu() for t in ops.nn_distance_idx(a.to(dev), b.to(dev))]
+    e1, j1, e2, j2 = cpu_nn(oracle_nn, a, b)
+    assert torch.equal(i1, j1) and torch.equal(i2, j2)
+    assert torch.equal(d1, e1) and torch.equal(d2, e2)  # bit-exact distances
+
+
+def test_nn_distance_reference_unit_test_and_ties(dev):
+    """ChamferDistancePytorch/unit_test.py:22-33 criterion on the golden inputs; duplicated points tie to lowest index."""
+    from ldt_b200 import ops
+    g = golden("nn.npz")
+    d1, i1, d2, i2 = [t.cpu() for t in ops.nn_distance_idx(g["p1"].to(dev), g["p2"].to(dev))]
+    assert float(((d1 - g["dist1"]) ** 2).mean() + ((d2 - g["dist2"]) ** 2).mean()) < 1e-8
+    assert float((i1 - g["idx1"]).float().norm() + (i2 - g["idx2"]).float().norm()) == 0.0
+    d1, i1, d2, i2 = [t.cpu() for t in ops.nn_distance_idx(g["q1"].to(dev), g["q2"].to(dev))]
+    assert torch.equal(i1[:, :5], torch.arange(5, dtype=torch.int32).expand(2, 5)) and torch.all(d1[:, :5] == 0)
+
+
+def test_nn_distance_bit_exact_vs_reference_cuda_kernel(dev):
+    """The reference's own NmDistanceKernel (compiled from its source into oracle/_ref) on the same GPU."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_nnd.so")
+    assert os.path.exists(path), "oracle/_ref/libref_nnd.so missing: run `make -C oracle` in the build container"
+    R = C.CDLL(path)
+    fn = getattr(R, "_Z10nndistanceiiPKfiS0_PfPiS1_S2_P11CUstream_st")  # nndistance(...), nndistance.cu:125
+    fn.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_void_p] * 5
+    from ldt_b200 import ops
+    for bs, n, m in [(8, 2048, 2048), (3, 700, 1500), (33, 64, 64)]:
+        g = torch.Generator().manual_seed(bs + n)
+        a = torch.randn((bs, n, 3), generator=g).to(dev)
+        b = (torch.randn((bs, m, 3), generator=g) * 0.7).to(dev)
+        r1, r2 = torch.empty((bs, n), device=dev), torch.empty((bs, m), device=dev)
+        k1 = torch.empty((bs, n), dtype=torch.int32, device=dev)
+        k2 = torch.empty((bs, m), dtype=torch.int32, device=dev)
+        fn(bs, n, a.data_ptr(), m, b.data_ptr(), r1.data_ptr(), k1.data_ptr(), r2.data_ptr(), k2.data_ptr(),
+           torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        d1, i1, d2, i2 = ops.nn_distance_idx(a, b)
+        assert torch.equal(i1, k1) and torch.equal(i2, k2)
+        assert torch.equal(d1, r1) and torch.equal(d2, r2)
+
+
+def test_nn_distance_rejects_bad_inputs(dev):
+    from ldt_b200 import ops
+    a = torch.rand(2, 8, 3, device=dev)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        ops.nn_distance_idx(a.transpose(0, 1), a)
+    with pytest.raises(RuntimeError):
+        ops.nn_distance_idx(a.double(), a)
+    with pytest.raises(RuntimeError, match="empty"):
+        ops.nn_distance_idx(a, torch.rand(2, 0, 3, device=dev))
+
+
+def test_pairwise_cd_vs_oracle_and_nn_kernel(dev, oracle_nn):
+    from ldt_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn((7, 300, 3), generator=g)
+    b = torch.randn((5, 173, 3), generator=g)
+    M = ops.pairwise_cd(a.to(dev), b.to(dev)).cpu()
+    ref = torch.empty(7, 5)
+    oracle_nn.oracle_pairwise_cd(7, 5, 300, 173, a.data_ptr(), b.data_ptr(), 0, 7, ref.data_ptr(), 4)
+    assert torch.allclose(M, ref, rtol=3e-7, atol=0)  # same minima; the sums are both double-accumulated
+    # row blocks compose (the multi-GPU sharding unit) and single rows equal the batched NN kernel + means
+    blk = ops.pairwise_cd(a.to(dev), b.to(dev), 2, 5).cpu()
+    assert torch.equal(blk, M[2:5])
+    d1, _, d2, _ = ops.nn_distance_idx(a[3:4].expand(5, -1, -1).contiguous().to(dev), b.to(dev))
+    row = (d1.double().mean(1).float() + d2.double().mean(1).float()).cpu()
+    assert torch.equal(row, M[3])
+
+
+def test_pairwise_cd_full_size_properties(dev):
+    """BASELINE config-4 point counts (2048 pts): symmetry, zero diagonal, permutation invariance, shard consistency."""
+    from ldt_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn((24, 2048, 3), generator=g)
+    x = x - x.mean(1, keepdim=True)
+    x = (x / x.norm(dim=-1).amax(1)[:, None, None]).to(dev)  # unit-sphere normalisation like ShapeNet_55.py:50-54
+    M = ops.pairwise_cd(x, x)
+    assert torch.equal(M, M.t())
+    assert torch.all(M.diagonal() == 0)
+    perm = torch.randperm(2048, generator=g).to(dev)
+    assert torch.allclose(ops.pairwise_cd(x[:, perm].contiguous(), x), M, rtol=1e-6, atol=0)
+    assert torch.equal(torch.cat([ops.pairwise_cd(x, x, 0, 11), ops.pairwise_cd(x, x, 11, 24)]), M)
+    assert torch.all(M[~torch.eye(24, dtype=torch.bool, device=dev)] > 0)
+
+
+def test_cd_metrics_match_reference_golden(dev):
+    from ldt_b200 import metrics
+    g = golden("metrics.npz")
+    res = metrics.compute_CD_metrics(g["smp"].to(dev), g["ref"].to(dev), 4)
+    assert float(res["mmd-CD"]) == pytest.approx(float(g["mmd"]), rel=1e-4)
+    assert float(res["cov-CD"]) == float(g["cov"])
+    assert float(res["1-NN-CD-acc"]) == float(g["acc"])
+    M_rs = metrics._pairwise_CD_(g["ref"].to(dev), g["smp"].to(dev), 4).cpu()
+    assert torch.allclose(M_rs, g["M_rs"], rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM core
+# ------------------------------------------------------------------------------------------------
+def _gemm_ref(A, W, bias, epi, resid=None, gate=None, rows_per_gate=1):
+    acc = A.float() @ W.float().t() + bias
+    if epi == 2:
+        acc = torch.nn.functional.gelu(acc)
+    if epi == 3:
+        g = 1.0 if gate is None else gate.repeat_interleave(rows_per_gate, dim=0)[: acc.shape[0]]
+        acc = resid + g * acc
+    return acc
+
+
+@pytest.mark.parametrize("backend", [0, 1])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 128, 256), (256, 512, 1024), (64, 120, 1024), (200, 1024, 128),
+                                   (4096, 3072, 1024), (1000, 149504 // 8, 1024), (96, 8, 128)])
+def test_gemm_all_epilogues(dev, backend, M, N, K):
+    from ldt_b200 import ops
+    if backend == 1 and M * N * K > 2 ** 31:
+        pytest.skip("naive cross-check kernel: skip the largest shapes")
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn((M, K), generator=g) * 0.5).to(dev).bfloat16()
+    W = (torch.randn((N, K), generator=g) / K ** 0.5).to(dev).bfloat16()
+    bias = torch.randn((N,), generator=g).to(dev)
+    ldo = (N + 7) // 8 * 8
+    for epi, dt in ((0, torch.float32), (1, torch.bfloat16), (2, torch.bfloat16), (3, torch.float32)):
+        out = torch.full((M, ldo), 7.0, dtype=dt, device=dev)
+        kw = {}
+        resid = gate = None
+        rpg = 32
+        if epi == 3:
+            resid = torch.randn((M, ldo), generator=g).to(dev)
+            gate = torch.randn(((M + rpg - 1) // rpg, N), generator=g).to(dev)
+            out = resid.clone()
+            kw = dict(resid=out, gate=gate, gate_stride=N, rows_per_gate=rpg)
+        ops.gemm(A, W, bias, out, epi, N=N, K=K, backend=backend, **kw)
+        ref = _gemm_ref(A, W, bias, epi, None if resid is None else resid[:, :N], gate, rpg)
+        got = out[:, :N].float()
+        if dt == torch.bfloat16:
+            assert_bf16_close(got, ref, 1e-4, f"backend {backend} epi {epi}")
+        else:  # fp32 output of exact bf16 products accumulated in fp32: only summation order differs
+            err = rel_rms_err(got, ref)
+            assert err < 1e-4, f"backend {backend} epi {epi}: rel err {err}"
+        if ldo > N and epi != 3:
+            assert torch.all(out[:, N:].float() == 7.0), "wrote outside the N columns"
+
+
+def test_gemm_tcgen05_matches_cross_check_bitwise_on_exact_inputs(dev):
+    """Small-integer inputs make every product and partial sum exact, so tcgen05, the SIMT cross-check and fp64
+    must agree to the bit: catches descriptor / swizzle / K-advance mistakes that tolerance tests can hide."""
+    from ldt_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    for M, N, K in [(128, 256, 64), (384, 256, 512), (130, 136, 192), (8192, 1024, 1024)]:
+        A = torch.randint(-4, 5, (M, K), generator=g).float().to(dev).bfloat16()
+        W = torch.randint(-4, 5, (N, K), generator=g).float().to(dev).bfloat16()
+        bias = torch.randint(-8, 9, (N,), generator=g).float().to(dev)
+        o0 = torch.empty((M, N), device=dev)
+        ops.gemm(A, W, bias, o0, 0, backend=0)
+        ref = (A.double() @ W.double().t() + bias.double()).float()
+        assert torch.equal(o0, ref), f"tcgen05 GEMM wrong at {M}x{N}x{K}: max diff {(o0 - ref).abs().max()}"
+        if M * N * K <= 2 ** 28:
+            o1 = torch.empty((M, N), device=dev)
+            ops.gemm(A, W, bias, o1, 0, backend=1)
+            assert torch.equal(o1, ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# element-wise kernels
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,C_", [(64, 128), (96, 1024), (8192, 1024), (33, 256)])
+def test_layernorm_modulate(dev, rows, C_):
+    from ldt_b200 import ops
+    g = torch.Generator().manual_seed(rows + C_)
+    x = (torch.randn((rows, C_), generator=g) * 3 + 1).to(dev)
+    nb = (rows + 31) // 32
+    mod = torch.randn((nb, 3 * C_), generator=g).to(dev)
+    y = torch.empty((rows, C_), dtype=torch.bfloat16, device=dev)
+    ops.layernorm_mod(x, y, shift=mod[:, :C_], scale=mod[:, C_:2 * C_], mod_stride=3 * C_, rows_per_mod=32)
+    n = torch.nn.functional.layer_norm(x, (C_,), eps=1e-6)
+    sh = mod[:, :C_].repeat_interleave(32, 0)[:rows]
+    sc = mod[:, C_:2 * C_].repeat_interleave(32, 0)[:rows]
+    ref = n * (1 + sc) + sh  # modulate(), model/layers.py:136-137
+    assert_bf16_close(y.float(), ref, 1e-5, "adaLN")
+    # broadcast (stride 0) AdaLN row and the affine flavour used by the decoder blocks
+    ops.layernorm_mod(x, y, shift=mod[:1, :C_], scale=mod[:1, C_:2 * C_], mod_stride=0, rows_per_mod=32)
+    assert_bf16_close(y.float(), n * (1 + mod[0, C_:2 * C_]) + mod[0, :C_], 1e-5, "adaLN broadcast")
+    w, b = mod[0, :C_].contiguous(), mod[0, C_:2 * C_].contiguous()
+    ops.layernorm_mod(x, y, weight=w, bias=b)
+    assert_bf16_close(y.float(), torch.nn.functional.layer_norm(x, (C_,), w, b, 1e-6), 1e-5, "affine")
+
+
+def test_cast_pad(dev):
+    from ldt_b200 import ops
+    x = torch.randn(96, 120, device=dev)
+    y = ops.cast_pad_bf16(x, 128)
+    assert torch.equal(y[:, :120], x.bfloat16()) and torch.all(y[:, 120:] == 0)
+    w = ops.pack_weight(torch.randn(40, 20, 1, device=dev))
+    assert w.shape == (40, 64) and torch.all(w[:, 20:] == 0)
+
+
+def test_time_embedding_vs_oracle(dev):
+    from ldt_b200 import ops
+    D, half = 256, 32
+    g = torch.Generator().manual_seed(2)
+    sd = O.synth_state_dict({"TimeEmbedding.mlp.0.weight": (D, 2 * half), "TimeEmbedding.mlp.0.bias": (D,),
+                             "TimeEmbedding.mlp.2.weight": (D, D), "TimeEmbedding.mlp.2.bias": (D,)}, 4)
+    for R in (1, 5, 16, 300):
+        t = torch.rand((R,), generator=g) * (1 - 1e-6) + 1e-6
+        ref = O.time_embedding(sd, t)
+        c = torch.empty((R, D), device=dev)
+        sc = torch.empty((R, D), dtype=torch.bfloat16, device=dev)
+        scratch = torch.empty((R, D + 2 * half), device=dev)
+        ops.time_embedding(t.to(dev), O.time_freq(2 * half).to(dev), sd["TimeEmbedding.mlp.0.weight"].to(dev),
+                           sd["TimeEmbedding.mlp.0.bias"].to(dev), sd["TimeEmbedding.mlp.2.weight"].to(dev),
+                           sd["TimeEmbedding.mlp.2.bias"].to(dev), None, c, sc, scratch)
+        assert rel_rms_err(c, ref) < 1e-5, rel_rms_err(c, ref)
+        assert_bf16_close(sc.float(), torch.nn.functional.silu(ref), 1e-5, "silu(c)")
+    extra = torch.randn((300, D), generator=g)
+    ops.time_embedding(t.to(dev), O.time_freq(2 * half).to(dev), sd["TimeEmbedding.mlp.0.weight"].to(dev),
+                       sd["TimeEmbedding.mlp.0.bias"].to(dev), sd["TimeEmbedding.mlp.2.weight"].to(dev),
+                       sd["TimeEmbedding.mlp.2.bias"].to(dev), extra.to(dev), c, sc, scratch)
+    assert rel_rms_err(c, ref + extra) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,Nq,dh", [(3, 16, 32, 64), (2, 4, 2048, 32), (2, 4, 1000, 32), (5, 2, 32, 64)])
+def test_attention_with_reference_layout_quirk(dev, B, H, Nq, dh):
+    from ldt_b200 import ops
+    C_ = H * dh
+    g = torch.Generator().manual_seed(B * Nq)
+    q = (torch.randn((B * Nq, C_), generator=g)).to(dev).bfloat16()
+    kv = (torch.randn((B * 32, 2 * C_), generator=g)).to(dev).bfloat16()
+    o = torch.empty((B * Nq, C_), dtype=torch.bfloat16, device=dev)
+    from ldt_b200.score import _PtrView
+    ops.attention_nk32(B, H, Nq, dh, q, C_, kv, _PtrView(kv.data_ptr() + 2 * C_), 2 * C_, o)
+    # oracle semantics (model/layers.py:192-197) on the same bf16-rounded operands, channels-first
+    qf = q.float().view(B, Nq, C_).transpose(1, 2)
+    kf = kv.float()[:, :C_].reshape(B, 32, C_).transpose(1, 2)
+    vf = kv.float()[:, C_:].reshape(B, 32, C_).transpose(1, 2)
+    qh = qf.reshape(B, H, dh, Nq).permute(0, 1, 3, 2)
+    kh = kf.reshape(B, H, dh, 32).permute(0, 1, 3, 2)
+    vh = vf.reshape(B, H, dh, 32).permute(0, 1, 3, 2)
+    w = ((qh @ kh.transpose(-2, -1)) * dh ** -0.5).softmax(-1)
+    ref = (w @ vh).reshape(B, Nq, C_)  # == the token-major buffer the next layer reads (quirk: no head permute)
+    # P is rounded to bf16 before P.V and the output once more: rms error ~2^-9, worst element a few times that
+    assert rms_rel_err(o.float().view(B, Nq, C_), ref) < 4e-3
+    assert rel_rms_err(o.float().view(B, Nq, C_), ref) < 3e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# SDE update kernel
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("pred", ["ancestral", "reversediffusion", "eulermaruyama", "ddim"])
+def test_sde_step_bit_exact_vs_oracle(dev, pred):
+    """Teacher-forced: same x, params, z and step scalars in => bit-identical x_next and x_mean as the reference's
+    op sequence (oracle restatement of diffusion_continuous.py:141-191 run on the same device with torch ops)."""
+    from ldt_b200 import DiffusionVPSDE, ops
+    from ldt_b200.sde import _PRED_CODES
+    cfg = ns(airplane_config()).sde
+    sde = DiffusionVPSDE(cfg, device=dev)
+    N = 1000
+    coef, ts = sde.step_coefficients(pred, N, 1e-6, False, dev)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn((4, 32, 120), generator=g).to(dev)
+    prm = torch.randn((4, 32, 120), generator=g).to(dev)
+    z = torch.randn((4, 32, 120), generator=g).to(dev)
+    osde = O.VPSDE(cfg.beta_start, cfg.beta_end, cfg.sigma2_0, cfg.sample_N)
+    # the reference builds its tables on the device (diffusion_continuous.py:649-653): cumprod must run there too
+    osde.betas = osde.betas.to(dev)
+    osde.alpha = 1.0 - osde.betas
+    osde.alphas_cump = osde.alpha.cumprod(dim=0)
+    for i in (0, 1, 10, 500, 998, 999):
+        step = torch.tensor([i], dtype=torch.int32, device=dev)
+        xn, xm = torch.empty_like(x), torch.empty_like(x)
+        ops.sde_step(_PRED_CODES[pred], x, prm, z, coef, step, 0, 0, 0, 0, xn, xm)
+        t = torch.ones(4, device=dev) * ts[i]
+        if pred == "ancestral":
+            rn, rm = O.ancestral_step(osde, x, t, prm, z, N)
+        elif pred == "reversediffusion":
+            rn, rm = O.reverse_diffusion_step(osde, x, t, prm, z, N, 1e-6)
+        elif pred == "eulermaruyama":
+            rn, rm = O.euler_maruyama_step(osde, x, t, prm, z, N)
+        else:
+            rn, rm = O.ddim_step(osde, x, t, prm, N)
+        assert torch.equal(xm, rm), f"{pred} step {i}: x_mean differs by {(xm - rm).abs().max()}"
+        assert torch.equal(xn, rn), f"{pred} step {i}: x differs by {(xn - rn).abs().max()}"
+
+
+@pytest.mark.parametrize("numel_shape", [(2, 32, 120), (16, 32, 120), (256, 32, 120), (333, 32, 120)])
+def test_sde_step_philox_noise_equals_torch_randn_like(dev, numel_shape):
+    """With z == NULL the kernel's in-kernel Philox normals must equal torch.randn_like from the same generator
+    state -- the reference draws its per-step noise that way (diffusion_continuous.py:160)."""
+    from ldt_b200 import ops
+    from ldt_b200.sde import torch_randn_launch_geometry
+    x = torch.zeros(numel_shape, device=dev)
+    prm = torch.zeros_like(x)
+    coef = torch.zeros((1, 8), device=dev)
+    coef[0, 0], coef[0, 1], coef[0, 2], coef[0, 3] = 1.0, 0.0, 1.0, 1.0  # ancestral with beta -> x_next = z exactly
+    gen = torch.cuda.default_generators[0]
+    torch.cuda.manual_seed(1234)
+    seed, off = gen.initial_seed(), gen.get_offset()
+    want = torch.randn_like(x)
+    grid, per_call = torch_randn_launch_geometry(x.numel(), dev)
+    assert gen.get_offset() - off == per_call, (gen.get_offset() - off, per_call)
+    xn = torch.empty_like(x)
+    ops.sde_step(0, x, prm, None, coef, None, seed, off, per_call, grid, xn, None)
+    assert torch.equal(xn, want), f"max diff {(xn - want).abs().max()}"
+    # second draw: offset advanced by per_call, selected through the device-side step index
+    want2 = torch.randn_like(x)
+    step = torch.ones(1, dtype=torch.int32, device=dev)
+    coef2 = coef.repeat(2, 1)
+    ops.sde_step(0, x, prm, None, coef2, step, seed, off, per_call, grid, xn, None)
+    assert torch.equal(xn, want2)
