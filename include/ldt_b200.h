@@ -86,10 +86,18 @@ typedef struct ldt_gemm_args {
                          gate_stride; gate_stride == 0 broadcasts one row */
   long long gate_stride;
   int rows_per_gate;
-  int backend;     /* 0 = tcgen05/TMEM/TMA kernel (product path); 1 = mma.sync cross-check kernel */
+  int backend;     /* 0 = tcgen05/TMEM/TMA kernel, tile shape chosen by the library (product path);
+                      1 = naive SIMT cross-check kernel (tests only);
+                      2 = force single-CTA 128-row tiles; 3 = force CTA-pair (cta_group::2) 256-row tiles */
 } ldt_gemm_args;
 
 int ldt_gemm_bf16(const ldt_gemm_args* args, void* stream);
+
+/* Diagnostics: when dev_buf != NULL, every CTA of the CTA-pair GEMM kernel writes 8 u64 stall counters
+ * (clock64 ticks) at dev_buf[8*blockIdx.x ...]: [0] MMA thread total, [1] its wait for TMA data, [2] its wait for
+ * a free accumulator, [3] epilogue warp total, [4] its wait for the accumulator, [5] TMA producer wait for a free
+ * stage, [6] producer total, [7] tiles.  dev_buf must hold 8 * gridDim u64 (<= 8 * SM count).  NULL switches it off. */
+int ldt_debug_set_gemm_counters(unsigned long long* dev_buf);
 
 /* ------------------------------------------------------------------------------------------------
  * Element-wise / normalisation kernels of the score net and decoder

@@ -29,6 +29,7 @@ struct EpiParams {
   const float* gate;
   long long gate_stride;
   int rows_per_gate;
+  unsigned long long* dbg;  // optional per-CTA stall counters (ldt_debug_set_gemm_counters), else nullptr
 };
 
 // One thread finishes 32 consecutive columns [col0, col0+32) of output row `row`.
@@ -105,6 +106,135 @@ __device__ __forceinline__ void epilogue_row32(const EpiParams& p, int row, int 
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (col0 + j < p.N) o[j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Staged epilogue for the tcgen05 kernels.  tcgen05.ld 32x32b hands every lane ONE output row, so storing straight
+// from registers makes each warp-wide store touch 32 different rows (16 B of every 32 B sector): measured, that
+// epilogue took 11-15 k cycles per 128x256 tile against an 8 k-cycle mainloop and throttled the tensor pipe.  Here
+// each warp transposes a 32-row x 128-byte unit through a private 4 KB shared-memory buffer (16-byte chunks XOR-
+// swizzled by row, conflict-free both ways) so that 8 lanes cover one full 128-byte row segment: residual loads and
+// output stores are fully coalesced (4 rows x 128 B per instruction).
+//   fp32 outputs: unit = 32 columns;  bf16 outputs: unit = 64 columns (bias/GELU applied before the transpose).
+// `taddr` is the TMEM address of (lane quadrant base, first column of this warp's slab); `ncols` columns are drained.
+// ------------------------------------------------------------------------------------------------
+constexpr int EPI_STG_BYTES = 4096;  // per warp
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_staged(const EpiParams& p, uint8_t* stg, int lane, int row_base, int col_base,
+                                                int ncols, uint32_t taddr) {
+  const uint32_t stg_u32 = smem_u32(stg);
+  const uint32_t st_row = stg_u32 + static_cast<uint32_t>(lane) * 128u;   // staging row written by this lane
+  const int rr0 = lane >> 3, cc = lane & 7;                                // read-back: row rr0 + 4*i, chunk cc
+  if constexpr (EPI == LDT_EPI_BIAS_F32 || EPI == LDT_EPI_GATE_RESID_F32) {
+    // one gate row for the whole 32-row slab (rows_per_gate a multiple of 32, e.g. the 32 latent tokens of a sample)?
+    const bool gate_uniform = (p.rows_per_gate & 31) == 0 && (row_base & 31) == 0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
+      if (col_base + c0 >= p.N) break;
+      const int col = col_base + c0 + cc * 4;
+      const bool col_ok = col < p.N;   // N % 8 == 0 and col % 4 == 0: the whole float4 is inside
+      // residual / gate / bias first: independent of the accumulator, so their latency hides behind the TMEM drain.
+      // (out may alias resid element for element; all loads of a unit are issued before its first store.)
+      float4 r4[8];
+      float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (EPI == LDT_EPI_GATE_RESID_F32) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = row_base + rr0 + 4 * i;
+          r4[i] = (col_ok && row < p.M)
+                      ? __ldcg(reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(row) * p.ldo + col))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (col_ok && p.gate != nullptr && gate_uniform)
+          g4 = __ldg(reinterpret_cast<const float4*>(
+              p.gate + static_cast<long long>(row_base / p.rows_per_gate) * p.gate_stride + col));
+      }
+      if (col_ok && p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t a = st_row + static_cast<uint32_t>((c ^ (lane & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * c]), "r"(v[4 * c + 1]),
+                     "r"(v[4 * c + 2]), "r"(v[4 * c + 3])
+                     : "memory");
+      }
+      __syncwarp();
+      if (col_ok) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = rr0 + 4 * i;
+          const int row = row_base + rr;
+          float4 a4;
+          const uint32_t a = stg_u32 + static_cast<uint32_t>(rr * 128 + ((cc ^ (rr & 7)) << 4));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w) : "r"(a));
+          if (row < p.M) {
+            a4.x += b4.x; a4.y += b4.y; a4.z += b4.z; a4.w += b4.w;
+            if constexpr (EPI == LDT_EPI_GATE_RESID_F32) {
+              float4 g = g4;
+              if (p.gate != nullptr && !gate_uniform)
+                g = __ldg(reinterpret_cast<const float4*>(
+                    p.gate + static_cast<long long>(row / p.rows_per_gate) * p.gate_stride + col));
+              a4.x = r4[i].x + g.x * a4.x; a4.y = r4[i].y + g.y * a4.y;
+              a4.z = r4[i].z + g.z * a4.z; a4.w = r4[i].w + g.w * a4.w;
+            }
+            *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col) = a4;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+#pragma unroll 1
+    for (int c0 = 0; c0 < ncols; c0 += 64) {
+      if (col_base + c0 >= p.N) break;
+      uint32_t v[64];
+      {
+        uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+        uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+        tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), lo);
+        if (c0 + 32 < ncols) tmem_ld_32x32(taddr + static_cast<uint32_t>(c0 + 32), hi);
+        tmem_ld_wait();
+      }
+      const int colb = col_base + c0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {   // 8 columns -> one 16-byte chunk of bf16
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[8 * c + j]);
+        if (p.bias != nullptr && colb + 8 * c < p.N) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + colb + 8 * c));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + colb + 8 * c + 4));
+          f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+        }
+        if constexpr (EPI == LDT_EPI_BIAS_GELU_BF16) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = gelu_erf_fast(f[j]);
+        }
+        const uint32_t a = st_row + static_cast<uint32_t>((c ^ (lane & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(f[0], f[1])),
+                     "r"(pack_bf16x2(f[2], f[3])), "r"(pack_bf16x2(f[4], f[5])), "r"(pack_bf16x2(f[6], f[7]))
+                     : "memory");
+      }
+      __syncwarp();
+      const int col = colb + cc * 8;
+      if (col < p.N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = rr0 + 4 * i;
+          const int row = row_base + rr;
+          uint4 u;
+          const uint32_t a = stg_u32 + static_cast<uint32_t>(rr * 128 + ((cc ^ (rr & 7)) << 4));
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(a));
+          if (row < p.M)
+            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col) = u;
+        }
+      }
+      __syncwarp();
     }
   }
 }
@@ -252,6 +382,183 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// tcgen05 kernel, CTA-pair version (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x BN tile.
+// Each CTA stages its own 128 rows of A and HALF of the W tile (BN/2 rows), the leader CTA's single MMA thread
+// issues tcgen05.mma.cta_group::2 (UMMA 256 x BN x 16) that reads both CTAs' shared memory and writes both CTAs'
+// TMEM.  Per CTA this halves the W bytes pulled from L2 per FLOP (128 -> 256 rows of output per W row), which is
+// what bounds the single-CTA kernel: 85 FLOP per L2 byte at 128x256 against ~12 TB/s of L2->SM bandwidth.
+//   full[s]   (leader's copy used)  TMA bytes of BOTH CTAs land on the leader's barrier
+//   empty[s]  (both copies)         tcgen05.commit multicast from the leader: the slot is free in both CTAs
+//   tfull[a]  (both copies)         accumulator a complete -> both CTAs' epilogue warps
+//   tempty[a] (leader's copy)       16 arrivals: 8 epilogue warps x 2 CTAs (the peer arrives remotely)
+// ------------------------------------------------------------------------------------------------
+constexpr int T2_BM = 256;
+
+template <int BN>
+struct Tc2Cfg {
+  static constexpr int A_BYTES = 128 * TC_BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * TC_BK * 2;
+  static constexpr int STAGES = (BN == 256) ? 6 : 8;
+  static constexpr int ACC_STRIDE = (BN > 128) ? 256 : 128;   // column offset between the two accumulators
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES =
+      1024 /*align slack*/ + STAGES * (A_BYTES + B_BYTES) + 256 /*barriers*/ + 8 * EPI_STG_BYTES /*epilogue staging*/;
+};
+
+template <int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const EpiParams p,
+                const int K, const int tiles_m, const int tiles_n) {
+  using Cfg = Tc2Cfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* stg_all = reinterpret_cast<uint8_t*>(full) + 256;   // 8 epilogue warps x EPI_STG_BYTES
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs), 1 = peer
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = K / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 16);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      long long t_begin = clock64(), t_wait = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile % tiles_m) * T2_BM + static_cast<int>(rank) * 128;
+        const int n0 = (tile / tiles_m) * BN + static_cast<int>(rank) * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const long long w0 = clock64();
+          mbar_wait(&empty[stage], phase ^ 1u);
+          t_wait += clock64() - w0;
+          const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);   // the leader's barrier
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+          tma_load_2d_pair(sA + stage * Cfg::A_BYTES, &tmA, bar, kb * TC_BK, m0);
+          tma_load_2d_pair(sB + stage * Cfg::B_BYTES, &tmW, bar, kb * TC_BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 8 + 5] = t_wait;
+        p.dbg[blockIdx.x * 8 + 6] = clock64() - t_begin;
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(T2_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      long long t_begin = clock64(), t_full = 0, t_tempty = 0, ntile = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        long long w0 = clock64();
+        mbar_wait(&tempty[acc], acc_phase ^ 1u);
+        t_tempty += clock64() - w0;
+        ++ntile;
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * Cfg::ACC_STRIDE);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          w0 = clock64();
+          mbar_wait(&full[stage], phase);
+          t_full += clock64() - w0;
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            umma_bf16_ss_pair(tmem_d, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
+                              (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_pair(&empty[stage], 0x3);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(&tfull[acc], 0x3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;
+        p.dbg[blockIdx.x * 8 + 1] = t_full;
+        p.dbg[blockIdx.x * 8 + 2] = t_tempty;
+        p.dbg[blockIdx.x * 8 + 7] = ntile;
+      }
+    }
+  } else if (warp >= TC_EPI_WARP0) {
+    const int quad = warp & 3;
+    const int half = (warp - TC_EPI_WARP0) >> 2;
+    uint8_t* stg = stg_all + (warp - TC_EPI_WARP0) * EPI_STG_BYTES;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    long long t_begin = clock64(), t_tfull = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m0 = (tile % tiles_m) * T2_BM + static_cast<int>(rank) * 128;
+      const int n0 = (tile / tiles_m) * BN;
+      const long long w0 = clock64();
+      mbar_wait(&tfull[acc], acc_phase);
+      t_tfull += clock64() - w0;
+      tc_fence_after();
+      {
+        const int col = half * (BN / 2);
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * Cfg::ACC_STRIDE + col);
+        epilogue_staged<EPI>(p, stg, lane, m0 + quad * 32, n0 + col, BN / 2, taddr);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (p.dbg && warp == TC_EPI_WARP0 && lane == 0) {
+      p.dbg[blockIdx.x * 8 + 3] = clock64() - t_begin;
+      p.dbg[blockIdx.x * 8 + 4] = t_tfull;
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();   // the peer's TMEM / shared memory stay valid until the leader's last MMA has retired
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Naive SIMT cross-check kernel (tests only): one warp per (row, 32-column chunk).
 // ------------------------------------------------------------------------------------------------
 template <int EPI>
@@ -342,6 +649,27 @@ static int launch_tc(const ldt_gemm_args& a, const EpiParams& p, cudaStream_t s)
   return LDT_OK;
 }
 
+template <int BN, int EPI>
+static int launch_tc2(const ldt_gemm_args& a, const EpiParams& p, cudaStream_t s) {
+  using Cfg = Tc2Cfg<BN>;
+  CUtensorMap tmA, tmW;
+  int rc = make_tmap_bf16(&tmA, a.A, a.M, a.K, a.lda, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tmW, a.W, a.N, a.K, a.ldw, BN / 2);
+  if (rc) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    LDT_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int tiles_m = (a.M + T2_BM - 1) / T2_BM;
+  const int tiles_n = (a.N + BN - 1) / BN;
+  const int pairs = min(tiles_m * tiles_n, num_sms() / 2);
+  gemm_tc2_kernel<BN, EPI><<<2 * pairs, TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmW, p, a.K, tiles_m, tiles_n);
+  LDT_CUDA_OK(cudaGetLastError());
+  return LDT_OK;
+}
+
 template <int EPI>
 static int launch_any(const ldt_gemm_args& a, const EpiParams& p, cudaStream_t s) {
   if (a.backend == 1) {
@@ -351,6 +679,12 @@ static int launch_any(const ldt_gemm_args& a, const EpiParams& p, cudaStream_t s
     LDT_CUDA_OK(cudaGetLastError());
     return LDT_OK;
   }
+  // backend 0 picks: CTA pairs (256-row tiles) once there are enough rows to fill them, else single-CTA tiles.
+  const bool pair_ok = (a.backend == 3) || (a.backend == 0 && a.M >= 1024);
+  if (pair_ok && a.backend != 2) {
+    if (a.N % 256 == 0) return launch_tc2<256, EPI>(a, p, s);
+    return launch_tc2<128, EPI>(a, p, s);
+  }
   if (a.N % 256 == 0) return launch_tc<256, EPI>(a, p, s);
   return launch_tc<128, EPI>(a, p, s);
 }
@@ -358,6 +692,12 @@ static int launch_any(const ldt_gemm_args& a, const EpiParams& p, cudaStream_t s
 }  // namespace ldt
 
 using namespace ldt;
+
+static unsigned long long* g_gemm_dbg = nullptr;
+extern "C" int ldt_debug_set_gemm_counters(unsigned long long* dev_buf) {
+  g_gemm_dbg = dev_buf;
+  return LDT_OK;
+}
 
 extern "C" int ldt_gemm_bf16(const ldt_gemm_args* args, void* stream) {
   LDT_REQUIRE(args != nullptr, LDT_ERR_INVALID, "ldt_gemm_bf16: null args");
@@ -377,6 +717,7 @@ extern "C" int ldt_gemm_bf16(const ldt_gemm_args* args, void* stream) {
   p.M = a.M; p.N = a.N; p.bias = a.bias; p.out = a.out; p.ldo = a.ldo;
   p.resid = a.resid; p.gate = a.gate; p.gate_stride = a.gate_stride;
   p.rows_per_gate = a.rows_per_gate > 0 ? a.rows_per_gate : 1;
+  p.dbg = g_gemm_dbg;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (a.epilogue) {
     case LDT_EPI_BIAS_F32: return launch_any<LDT_EPI_BIAS_F32>(a, p, s);

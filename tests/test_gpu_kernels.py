@@ -156,7 +156,7 @@ def _gemm_ref(A, W, bias, epi, resid=None, gate=None, rows_per_gate=1):
     return acc
 
 
-@pytest.mark.parametrize("backend", [0, 1])
+@pytest.mark.parametrize("backend", [0, 1, 2, 3])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 128, 256), (256, 512, 1024), (64, 120, 1024), (200, 1024, 128),
                                    (4096, 3072, 1024), (1000, 149504 // 8, 1024), (96, 8, 128)])
 def test_gemm_all_epilogues(dev, backend, M, N, K):
@@ -199,10 +199,11 @@ def test_gemm_tcgen05_matches_cross_check_bitwise_on_exact_inputs(dev):
         A = torch.randint(-4, 5, (M, K), generator=g).float().to(dev).bfloat16()
         W = torch.randint(-4, 5, (N, K), generator=g).float().to(dev).bfloat16()
         bias = torch.randint(-8, 9, (N,), generator=g).float().to(dev)
-        o0 = torch.empty((M, N), device=dev)
-        ops.gemm(A, W, bias, o0, 0, backend=0)
         ref = (A.double() @ W.double().t() + bias.double()).float()
-        assert torch.equal(o0, ref), f"tcgen05 GEMM wrong at {M}x{N}x{K}: max diff {(o0 - ref).abs().max()}"
+        for backend in (0, 2, 3):  # library's choice, single-CTA tiles, CTA-pair (cta_group::2) tiles
+            o0 = torch.empty((M, N), device=dev)
+            ops.gemm(A, W, bias, o0, 0, backend=backend)
+            assert torch.equal(o0, ref), f"tcgen05 GEMM (backend {backend}) wrong at {M}x{N}x{K}: max diff {(o0 - ref).abs().max()}"
         if M * N * K <= 2 ** 28:
             o1 = torch.empty((M, N), device=dev)
             ops.gemm(A, W, bias, o1, 0, backend=1)
