@@ -139,6 +139,18 @@ int ldt_time_embedding(int R, int half, int D, const float* t, const float* freq
 int ldt_attention_nk32(int B, int H, int Nq, int dh, const void* q, int ldq, const void* k, const void* v,
                        int ldkv, void* o, void* stream);
 
+/* Fused Q/K/V projection + self-attention of one score-net block (fc_q, fc_kv and compute_attention of
+ * model/layers.py:186-197 in one kernel; Q, K, V stay on chip).
+ *   A   bf16 [B*32, lda]   LayerNorm'd + modulated activations (K = hidden columns used)
+ *   Wp  bf16 [H*192, ldw]  projection weights packed HEAD-MAJOR: rows h*192+[0,64) = fc_q rows of head h,
+ *                          +[64,128) = the K rows of fc_kv, +[128,192) = its V rows (heads are contiguous
+ *                          64-channel groups, layers.py:192-194)
+ *   bias_p f32 [H*192] packed the same way, or NULL
+ *   out bf16 [B, H, 32, 64] contiguous == the reference's (w@v).reshape(B,N,C) buffer (layout quirk, :197)
+ * 32 tokens per sample, head dim 64 (the shipped score configuration); K a multiple of 64. */
+int ldt_qkv_attention_bf16(int B, int H, int K, const void* A, int lda, const void* Wp, int ldw, const float* bias_p,
+                           void* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Reverse-SDE predictor updates (diffusion/diffusion_continuous.py:141-191) fused with the score
  * conversion of Trainer.score_fn (trainer/Latent_SDE_Trainer.py:57-61):  score = -params / sqrt(var)

@@ -44,33 +44,35 @@ __global__ void __launch_bounds__(256) cast_pad_kernel(long long rows, int cols,
 // ------------------------------------------------------------------------------------------------
 constexpr int LN_MAXV = 16;  // float4 per lane => C <= 2048
 
-__global__ void __launch_bounds__(256) layernorm_mod_kernel(int rows, int C, const float* __restrict__ x,
+// NV = C / 128 float4 per lane, a compile-time constant so the row lives in exactly NV*4 registers: at C = 1024 the
+// kernel needs ~56 registers instead of the 96 a runtime-bounded v[16] costs, which more than doubles the resident
+// warps per SM; the kernel is latency-bound (one dependent chain load -> 2 reductions -> modulation loads -> store
+// per row), so resident warps are what hides it.  4 rows per 128-thread CTA keeps the tail wave short.
+template <int NV>
+__global__ void __launch_bounds__(128) layernorm_mod_kernel(int rows, const float* __restrict__ x,
                                                           const float* __restrict__ shift,
                                                           const float* __restrict__ scale, long long mod_stride,
                                                           int rows_per_mod, const float* __restrict__ weight,
                                                           const float* __restrict__ bias, float eps,
                                                           __nv_bfloat16* __restrict__ y) {
+  constexpr int C = NV * 128;
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const int nv = C >> 7;  // float4 per lane
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * C);
-  float4 v[LN_MAXV];
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = __ldcg(xr + i * 32 + lane);   // streamed once: keep it out of L1
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i)
-    if (i < nv) {
-      v[i] = xr[i * 32 + lane];
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   const float mean = warp_sum(s) / static_cast<float>(C);
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i)
-    if (i < nv) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      q += (a * a + b * b) + (c * c + d * d);
-    }
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
   const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(C) + eps);
   const float4* m_mul;
   const float4* m_add;
@@ -85,23 +87,22 @@ __global__ void __launch_bounds__(256) layernorm_mod_kernel(int rows, int C, con
   }
   uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * C);
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i)
-    if (i < nv) {
-      const int idx = i * 32 + lane;
-      float4 mu = make_float4(1.f, 1.f, 1.f, 1.f), ad = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m_mul) mu = __ldg(m_mul + idx);
-      if (m_add) ad = __ldg(m_add + idx);
-      if (ada) { mu.x += 1.f; mu.y += 1.f; mu.z += 1.f; mu.w += 1.f; }
-      const float o0 = (v[i].x - mean) * rstd * mu.x + ad.x;
-      const float o1 = (v[i].y - mean) * rstd * mu.y + ad.y;
-      const float o2 = (v[i].z - mean) * rstd * mu.z + ad.z;
-      const float o3 = (v[i].w - mean) * rstd * mu.w + ad.w;
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
-      uint2 u;
-      u.x = *reinterpret_cast<uint32_t*>(&h0);
-      u.y = *reinterpret_cast<uint32_t*>(&h1);
-      yr[idx] = u;
-    }
+  for (int i = 0; i < NV; ++i) {
+    const int idx = i * 32 + lane;
+    float4 mu = make_float4(1.f, 1.f, 1.f, 1.f), ad = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m_mul) mu = __ldg(m_mul + idx);
+    if (m_add) ad = __ldg(m_add + idx);
+    if (ada) { mu.x += 1.f; mu.y += 1.f; mu.z += 1.f; mu.w += 1.f; }
+    const float o0 = (v[i].x - mean) * rstd * mu.x + ad.x;
+    const float o1 = (v[i].y - mean) * rstd * mu.y + ad.y;
+    const float o2 = (v[i].z - mean) * rstd * mu.z + ad.z;
+    const float o3 = (v[i].w - mean) * rstd * mu.w + ad.w;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    yr[idx] = u;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -279,8 +280,20 @@ extern "C" int ldt_layernorm_mod_bf16(int rows, int C, const float* x, const flo
   LDT_REQUIRE(!(scale && weight), LDT_ERR_INVALID, "ldt_layernorm_mod_bf16: pass AdaLN (shift,scale) or affine (weight,bias), not both");
   LDT_REQUIRE(mod_stride % 4 == 0, LDT_ERR_INVALID, "ldt_layernorm_mod_bf16: mod_stride must be a multiple of 4");
   if (rows_per_mod <= 0) rows_per_mod = 1;
-  layernorm_mod_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      rows, C, x, shift, scale, mod_stride, rows_per_mod, weight, bias, eps, static_cast<__nv_bfloat16*>(y));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* yb = static_cast<__nv_bfloat16*>(y);
+  const int grid = (rows + 3) / 4;
+#define LDT_LN_CASE(NV)                                                                                              \
+  case NV:                                                                                                           \
+    layernorm_mod_kernel<NV><<<grid, 128, 0, s>>>(rows, x, shift, scale, mod_stride, rows_per_mod, weight, bias, eps, yb); \
+    break
+  switch (C / 128) {
+    LDT_LN_CASE(1); LDT_LN_CASE(2); LDT_LN_CASE(3); LDT_LN_CASE(4); LDT_LN_CASE(5); LDT_LN_CASE(6); LDT_LN_CASE(7);
+    LDT_LN_CASE(8); LDT_LN_CASE(9); LDT_LN_CASE(10); LDT_LN_CASE(11); LDT_LN_CASE(12); LDT_LN_CASE(13);
+    LDT_LN_CASE(14); LDT_LN_CASE(15); LDT_LN_CASE(16);
+    default: set_last_error("ldt_layernorm_mod_bf16: unsupported C=%d", C); return LDT_ERR_UNSUPPORTED;
+  }
+#undef LDT_LN_CASE
   LDT_CUDA_OK(cudaGetLastError());
   return LDT_OK;
 }

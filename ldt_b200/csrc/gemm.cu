@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "ldt_b200.h"
+#include "tmap.cuh"
 
 namespace ldt {
 
@@ -610,7 +611,7 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 // bf16 [rows, ld] row-major; tile box = box_rows x 64 columns, 128-byte swizzle, OOB reads give zero.
-static int make_tmap_bf16(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int box_rows) {
+int make_tmap_bf16(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int box_rows) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return LDT_ERR_CUDA;
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};

@@ -1,0 +1,374 @@
+// Fused self-attention front half of a score-net block:  LN'd activations -> Q/K/V projection -> per-head
+// softmax(q k^T / sqrt(dh)) v  in ONE kernel; Q, K, V never reach HBM.
+//
+// Replaces, for the self-attention blocks, fc_q + fc_kv (model/layers.py:186-189) and compute_attention's
+// permute/clone + bmm + mul + softmax + bmm (layers.py:192-197): 2 cuDNN convs + ~7 launches in the reference, and a
+// [M,3072] bf16 round trip plus a separate attention launch in this repo's unfused path (gemm.cu + attention.cu).
+//
+// Shape of the work: M = B*32 token rows, K = hidden (1024), 16 heads x dh 64.  The projection weight is packed head-
+// major (rows h*192 + [0,64) = q_h, [64,128) = k_h, [128,192) = v_h; score.py::packed), so one 256-row x 192-column
+// GEMM tile holds everything 8 samples need for one head.  32 x 16 = 512 tiles over 74 CTA pairs = 6.92 waves (the
+// plain N=3072 GEMM with 256-wide tiles quantises to 5.19 -> 6 waves).
+//
+// Kernel structure = the CTA-pair tcgen05 GEMM of gemm.cu (TMA producer warp, one MMA thread issuing
+// tcgen05.mma.cta_group::2 256x192x16, two TMEM accumulators) with a different epilogue: the 8 epilogue warps form two
+// sets; set s drains accumulator s (so every set has two mainloops of time per tile).  Warp (set, quad) owns TMEM lanes
+// 32*quad..+31 = the 32 tokens of ONE sample: it pulls Q,K (then V) out of TMEM, adds the bias, rounds to bf16 into a
+// private shared-memory tile, and runs the 32x32 attention with mma.sync m16n8k16 exactly like attention.cu.  The
+// output is written in the reference's layout quirk: [B,H,32,dh] contiguous, which the next layer re-reads as
+// token-major [B*32, H*dh] (layers.py:197).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ldt_b200.h"
+#include "mma_sync.cuh"
+#include "tmap.cuh"
+
+namespace ldt {
+
+constexpr int QA_BK = 64;
+constexpr int QA_DH = 64;
+constexpr int QA_BN = 3 * QA_DH;             // 192: q_h | k_h | v_h
+constexpr int QA_THREADS = 384;
+constexpr int QA_EPI_WARP0 = 4;
+constexpr int QA_A_BYTES = 128 * QA_BK * 2;  // 16 KB: this CTA's 128 rows
+constexpr int QA_B_BYTES = (QA_BN / 2) * QA_BK * 2;  // 12 KB: this CTA's half of the head's 192 weight rows
+constexpr int QA_STAGES = 5;
+constexpr int QA_ACC_STRIDE = 256;
+constexpr int QA_TMEM_COLS = 512;
+constexpr int QA_QK_LD = 2 * QA_DH + 8;      // bf16 elements per staged Q|K row (272 B: conflict-free fragment loads)
+constexpr int QA_V_LD = QA_DH + 8;           // bf16 elements per staged V / O row (144 B)
+constexpr int QA_STG_BYTES = 2 * 32 * QA_V_LD * 2;  // 9216 B per warp: Q|K tile (8704 B), later V tile + O tile (4608 B each)
+constexpr int QA_SMEM_BYTES = 1024 + QA_STAGES * (QA_A_BYTES + QA_B_BYTES) + 256 + 8 * QA_STG_BYTES + 16;
+
+struct QkvAttnParams {
+  int M;                 // token rows = B * 32
+  int H;                 // heads
+  const float* bias;     // [H * 192] head-major packed, or nullptr
+  __nv_bfloat16* out;    // [B, H, 32, 64] contiguous
+  float scale_log2e;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QA_THREADS, 1)
+qkv_attention_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                     const QkvAttnParams p, const int K, const int tiles_m) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + QA_STAGES * QA_A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + QA_STAGES * QA_B_BYTES);
+  uint64_t* empty = full + QA_STAGES;
+  uint64_t* tfull = empty + QA_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* stg_all = reinterpret_cast<uint8_t*>(full) + 256;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int num_tiles = tiles_m * p.H;
+  const int num_kb = K / QA_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < QA_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 8);   // 4 warps of one epilogue set x 2 CTAs
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, QA_TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile % tiles_m) * 256 + static_cast<int>(rank) * 128;
+        const int n0 = (tile / tiles_m) * QA_BN + static_cast<int>(rank) * (QA_BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * (QA_A_BYTES + QA_B_BYTES));
+          tma_load_2d_pair(sA + stage * QA_A_BYTES, &tmA, bar, kb * QA_BK, m0);
+          tma_load_2d_pair(sB + stage * QA_B_BYTES, &tmW, bar, kb * QA_BK, n0);
+          if (++stage == QA_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, QA_BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * QA_ACC_STRIDE);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * QA_A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * QA_B_BYTES);
+#pragma unroll
+          for (int k = 0; k < QA_BK / 16; ++k) {
+            umma_bf16_ss_pair(tmem_d, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
+                              (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_pair(&empty[stage], 0x3);
+          if (++stage == QA_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(&tfull[acc], 0x3);
+      }
+    }
+  } else if (warp >= QA_EPI_WARP0) {
+    const int quad = warp & 3;                       // TMEM lane quadrant = sample within this CTA's 4 samples
+    const int set = (warp - QA_EPI_WARP0) >> 2;      // which accumulator this warp drains
+    __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(stg_all + (warp - QA_EPI_WARP0) * QA_STG_BYTES);
+    const uint32_t stg_u32 = smem_u32(stg);
+    const int g = lane >> 2, t = lane & 3;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      if ((it & 1) != set) continue;
+      const int head = tile / tiles_m;
+      const int row0 = (tile % tiles_m) * 256 + static_cast<int>(rank) * 128 + quad * 32;   // first token row
+      mbar_wait(&tfull[set], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(set * QA_ACC_STRIDE);
+      const bool live = row0 < p.M;                  // whole samples only: M % 32 == 0
+      const float* bias = p.bias ? p.bias + head * QA_BN : nullptr;
+
+      // ---- Q | K : TMEM -> (+bias) -> bf16 -> staging rows [token = lane][128] ----
+#pragma unroll 1
+      for (int c = 0; c < 4; c += 2) {
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v0);
+        tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32 + 32), v1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const uint32_t(&v)[32] = hh ? v1 : v0;
+          const int col = (c + hh) * 32;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
+            if (bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col + 8 * j));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 8 * j + 4));
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            const uint32_t a = stg_u32 + static_cast<uint32_t>(lane * (QA_QK_LD * 2) + (col + 8 * j) * 2);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16(f[0], f[1])),
+                         "r"(pack_bf16(f[2], f[3])), "r"(pack_bf16(f[4], f[5])), "r"(pack_bf16(f[6], f[7]))
+                         : "memory");
+          }
+        }
+      }
+      // ---- V : TMEM -> registers now (so the accumulator can be handed back), staged after S is done ----
+      uint32_t vv0[32], vv1[32];
+      tmem_ld_32x32(taddr + 128u, vv0);
+      tmem_ld_32x32(taddr + 160u, vv1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[set]), 0));
+
+      // ---- S = Q K^T (32 x 32), fragments from the staged tile ----
+      float s[2][4][4];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) s[mi][ni][e] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < QA_DH / 16; ++ks) {
+        uint32_t a[2][4];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+          const __nv_bfloat16* q0 = stg + (mi * 16 + g) * QA_QK_LD + ks * 16 + 2 * t;
+          const __nv_bfloat16* q1 = q0 + 8 * QA_QK_LD;
+          a[mi][0] = ld_u32(q0);
+          a[mi][1] = ld_u32(q1);
+          a[mi][2] = ld_u32(q0 + 8);
+          a[mi][3] = ld_u32(q1 + 8);
+        }
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const __nv_bfloat16* kr = stg + (ni * 8 + g) * QA_QK_LD + QA_DH + ks * 16 + 2 * t;
+          const uint32_t b0 = ld_u32(kr), b1 = ld_u32(kr + 8);
+          mma_bf16_16816(s[0][ni], a[0], b0, b1);
+          mma_bf16_16816(s[1][ni], a[1], b0, b1);
+        }
+      }
+      __syncwarp();   // all lanes are done reading Q|K: the staging tile may be overwritten with V
+
+      // ---- stage V rows [token = lane][64] ----
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const uint32_t(&v)[32] = hh ? vv1 : vv0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
+          if (bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 128 + hh * 32 + 8 * j));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + 128 + hh * 32 + 8 * j + 4));
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+          }
+          const uint32_t a = stg_u32 + static_cast<uint32_t>(lane * (QA_V_LD * 2) + (hh * 32 + 8 * j) * 2);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16(f[0], f[1])),
+                       "r"(pack_bf16(f[2], f[3])), "r"(pack_bf16(f[4], f[5])), "r"(pack_bf16(f[6], f[7]))
+                       : "memory");
+        }
+      }
+
+      // ---- softmax over the 32 keys (rows g and g+8 of each 16-row tile), P rounded to bf16 ----
+      float inv_sum[2][2];
+      uint32_t pfrag[2][2][4];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          float m = -INFINITY;
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) m = fmaxf(m, fmaxf(s[mi][ni][2 * hh], s[mi][ni][2 * hh + 1]));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+          float sum = 0.f;
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) {
+            const float p0 = exp2f((s[mi][ni][2 * hh] - m) * p.scale_log2e);
+            const float p1 = exp2f((s[mi][ni][2 * hh + 1] - m) * p.scale_log2e);
+            s[mi][ni][2 * hh] = p0;
+            s[mi][ni][2 * hh + 1] = p1;
+            sum += p0 + p1;
+          }
+          sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+          sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+          inv_sum[mi][hh] = 1.0f / sum;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          pfrag[mi][j][0] = pack_bf16(s[mi][2 * j][0], s[mi][2 * j][1]);
+          pfrag[mi][j][1] = pack_bf16(s[mi][2 * j][2], s[mi][2 * j][3]);
+          pfrag[mi][j][2] = pack_bf16(s[mi][2 * j + 1][0], s[mi][2 * j + 1][1]);
+          pfrag[mi][j][3] = pack_bf16(s[mi][2 * j + 1][2], s[mi][2 * j + 1][3]);
+        }
+      }
+      __syncwarp();   // V tile complete
+
+      // ---- O = P V, staged as [token][64] bf16 behind the V tile, then written as one contiguous 4 KB block ----
+      __nv_bfloat16* so = stg + 32 * QA_V_LD;
+      const int mat = lane >> 3, r8 = lane & 7;
+#pragma unroll
+      for (int np = 0; np < QA_DH / 16; ++np) {
+        float acc[2][2][4];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int nn = 0; nn < 2; ++nn)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[mi][nn][e] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          uint32_t r0, r1, r2, r3;
+          const __nv_bfloat16* addr = stg + (16 * j + (mat & 1) * 8 + r8) * QA_V_LD + (2 * np + (mat >> 1)) * 8;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                       : "r"(smem_u32(addr)));
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) {
+            mma_bf16_16816(acc[mi][0], pfrag[mi][j], r0, r1);
+            mma_bf16_16816(acc[mi][1], pfrag[mi][j], r2, r3);
+          }
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int nn = 0; nn < 2; ++nn) {
+            const int col = (2 * np + nn) * 8 + 2 * t;
+            const int n0 = mi * 16 + g;
+            *reinterpret_cast<uint32_t*>(so + n0 * QA_V_LD + col) =
+                pack_bf16(acc[mi][nn][0] * inv_sum[mi][0], acc[mi][nn][1] * inv_sum[mi][0]);
+            *reinterpret_cast<uint32_t*>(so + (n0 + 8) * QA_V_LD + col) =
+                pack_bf16(acc[mi][nn][2] * inv_sum[mi][1], acc[mi][nn][3] * inv_sum[mi][1]);
+          }
+      }
+      __syncwarp();
+      if (live) {
+        const int b = row0 >> 5;
+        uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(b) * p.H + head) * (32 * QA_DH));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int id = i * 32 + lane;   // 16-byte chunk of the [32][64] bf16 tile
+          dst[id] = *reinterpret_cast<const uint4*>(so + (id >> 3) * QA_V_LD + (id & 7) * 8);
+        }
+      }
+      __syncwarp();   // staging is reused by this warp's next tile
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, QA_TMEM_COLS);
+  }
+}
+
+}  // namespace ldt
+
+using namespace ldt;
+
+extern "C" int ldt_qkv_attention_bf16(int B, int H, int K, const void* A, int lda, const void* Wp, int ldw,
+                                      const float* bias_p, void* out, void* stream) {
+  LDT_REQUIRE(B >= 0 && H > 0 && K > 0, LDT_ERR_INVALID, "ldt_qkv_attention_bf16: bad shape B=%d H=%d K=%d", B, H, K);
+  if (B == 0) return LDT_OK;
+  LDT_REQUIRE(K % QA_BK == 0, LDT_ERR_INVALID, "ldt_qkv_attention_bf16: K=%d must be a multiple of %d", K, QA_BK);
+  LDT_REQUIRE(lda >= K && ldw >= K && lda % 8 == 0 && ldw % 8 == 0, LDT_ERR_INVALID,
+              "ldt_qkv_attention_bf16: lda=%d ldw=%d must be >= K and multiples of 8", lda, ldw);
+  LDT_REQUIRE(A && Wp && out, LDT_ERR_INVALID, "ldt_qkv_attention_bf16: null pointer");
+  LDT_REQUIRE((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Wp) | reinterpret_cast<uintptr_t>(out) |
+               reinterpret_cast<uintptr_t>(bias_p)) % 16 == 0,
+              LDT_ERR_INVALID, "ldt_qkv_attention_bf16: pointers must be 16-byte aligned");
+  const int M = B * 32;
+  CUtensorMap tmA, tmW;
+  int rc = make_tmap_bf16(&tmA, A, M, K, lda, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tmW, Wp, H * QA_BN, K, ldw, QA_BN / 2);
+  if (rc) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    LDT_CUDA_OK(cudaFuncSetAttribute(qkv_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QA_SMEM_BYTES));
+    attr_done = true;
+  }
+  QkvAttnParams p;
+  p.M = M; p.H = H; p.bias = bias_p; p.out = static_cast<__nv_bfloat16*>(out);
+  p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(QA_DH));
+  const int tiles_m = (M + 255) / 256;
+  const int pairs = min(tiles_m * H, num_sms() / 2);
+  qkv_attention_kernel<<<2 * pairs, QA_THREADS, QA_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmA, tmW, p, K, tiles_m);
+  LDT_CUDA_OK(cudaGetLastError());
+  return LDT_OK;
+}

@@ -168,6 +168,14 @@ def attention_nk32(B: int, H: int, Nq: int, dh: int, q, ldq: int, k, v, ldkv: in
               "ldt_attention_nk32")
 
 
+def qkv_attention(B: int, H: int, A, Wp, bias_p, out) -> None:
+    """Fused head-major QKV projection + 32-token self-attention (ldt_qkv_attention_bf16)."""
+    K = A.shape[1]
+    with torch.cuda.device(out.device), _launch("qkv_attention", 1, (B * 32, 3 * 64 * H, K, -1)):
+        check(load().ldt_qkv_attention_bf16(B, H, K, ptr(A), A.stride(0), ptr(Wp), Wp.stride(0), ptr(bias_p), ptr(out),
+                                            stream_ptr()), "ldt_qkv_attention_bf16")
+
+
 def sde_step(predictor: int, x, params, z, coef_table, step_index, seed: int, offset: int, offset_per_step: int,
              rng_grid: int, x_next, x_mean) -> None:
     with torch.cuda.device(x.device), _launch("sde_step"):

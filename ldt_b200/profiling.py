@@ -6,7 +6,8 @@ import torch
 
 from . import ops
 
-FLOP_GEMM_PER_SAMPLE_STEP = 19.44e9 - 24 * 2 * 2 * 16 * 32 * 32 * 64  # SURVEY.md 8(d) minus QK^T/PV (attention kernel)
+FLOP_ATTN_PER_SAMPLE_STEP = 24 * 2 * 2 * 16 * 32 * 32 * 64             # QK^T + PV of the 24 blocks
+FLOP_GEMM_PER_SAMPLE_STEP = 19.44e9 - FLOP_ATTN_PER_SAMPLE_STEP        # SURVEY.md 8(d) minus QK^T/PV
 
 
 def profile_score_step(score, B: int, reps: int = 3) -> dict:
@@ -24,6 +25,7 @@ def profile_score_step(score, B: int, reps: int = 3) -> dict:
     by_kind: dict = {}
     gemm_ms = total_ms = 0.0
     gemm_launches = 0
+    fused = False
     for _ in range(reps):
         with ops.profile() as rec:
             score.run_tokens(P, ws, x, mod, 0, out)
@@ -33,8 +35,11 @@ def profile_score_step(score, B: int, reps: int = 3) -> dict:
                 key = kind if kind != "gemm" else f"gemm N={note[1]} K={note[2]}"
                 by_kind[key] = by_kind.get(key, 0.0) + ms / reps
                 total_ms += ms / reps
-                if kind == "gemm":
+                if kind in ("gemm", "qkv_attention"):   # the tcgen05 contraction kernels
                     gemm_ms += ms / reps
                     gemm_launches += 1
-    return {"gemm_ms": gemm_ms, "total_ms": total_ms, "gemm_flop": B * FLOP_GEMM_PER_SAMPLE_STEP,
+                if kind == "qkv_attention":
+                    fused = True
+    flop = B * (FLOP_GEMM_PER_SAMPLE_STEP + (FLOP_ATTN_PER_SAMPLE_STEP if fused else 0))
+    return {"gemm_ms": gemm_ms, "total_ms": total_ms, "gemm_flop": flop,
             "gemm_launches": gemm_launches // reps, "by_kind": {k: round(v, 4) for k, v in by_kind.items()}}

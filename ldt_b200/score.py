@@ -143,6 +143,9 @@ class Score(nn.Module):
         self._packed = None
         self._packed_key = None
         self._ws = {}
+        # self-attention blocks run the fused projection+attention kernel (head dim 64, 32 tokens); False selects the
+        # unfused GEMM + attention kernels (kept for cross-attention blocks and as a cross-check in the tests)
+        self.fused_attention = True
 
     # ------------------------------------------------------------------------------------------
     # weight packing (fp32 parameters -> bf16 K-major GEMM operands), invalidated when any parameter's
@@ -167,7 +170,15 @@ class Score(nn.Module):
             for blk in self.Transformer:
                 wq = torch.cat([blk.fc_q.weight.detach().reshape(self.hidden_size, -1),
                                 blk.fc_kv.weight.detach().reshape(2 * self.hidden_size, -1)], dim=0)
+                # head-major packing for the fused projection+attention kernel: [q_h | k_h | v_h] per head
+                dh = self.hidden_size // self.num_heads
+                Hn, Hd = self.num_heads, self.hidden_size
+                perm = torch.stack([torch.arange(Hn).view(Hn, 1) * dh + torch.arange(dh).view(1, dh) + off
+                                    for off in (0, Hd, 2 * Hd)], dim=1).reshape(-1).to(wq.device)
+                bq = torch.cat([blk.fc_q.bias.detach(), blk.fc_kv.bias.detach()]).float()
                 d = {
+                    "w_qkv_p": ops.pack_weight(wq[perm]) if dh == 64 else None,
+                    "b_qkv_p": bq[perm].contiguous() if dh == 64 else None,
                     "w_qkv": ops.pack_weight(wq),
                     "b_qkv": torch.cat([blk.fc_q.bias.detach(), blk.fc_kv.bias.detach()]).float().contiguous(),
                     "w_o": ops.pack_weight(blk.fc_o.weight), "b_o": blk.fc_o.bias.detach().float().contiguous(),
@@ -238,6 +249,8 @@ class Score(nn.Module):
                 ops.gemm(ws.a, W["w_qkv"], W["b_qkv"], ws.qkv, EPI_BIAS_BF16, N=Hd)
                 kc = kv_cond[i // 2]
                 ops.attention_nk32(B, heads, T, dh, q, 3 * Hd, kc, _PtrView(kc.data_ptr() + 2 * Hd), 2 * Hd, ws.att)
+            elif self.fused_attention and W["w_qkv_p"] is not None:
+                ops.qkv_attention(B, heads, ws.a, W["w_qkv_p"], W["b_qkv_p"], ws.att)
             else:
                 ops.gemm(ws.a, W["w_qkv"], W["b_qkv"], ws.qkv, EPI_BIAS_BF16)
                 ops.attention_nk32(B, heads, T, dh, q, 3 * Hd, k, v, 3 * Hd, ws.att)

@@ -292,6 +292,42 @@ def test_attention_with_reference_layout_quirk(dev, B, H, Nq, dh):
     assert rel_rms_err(o.float().view(B, Nq, C_), ref) < 3e-2
 
 
+@pytest.mark.parametrize("B", [1, 8, 13, 256])
+def test_fused_qkv_attention_equals_unfused_path(dev, B):
+    """ldt_qkv_attention_bf16 (head-major packed weights, attention in the GEMM epilogue) against the unfused
+    GEMM -> [M,3072] bf16 -> attention kernel pipeline on the same operands: same rounding points (q,k,v and the
+    softmax numerators rounded to bf16), so the two must agree to accumulation-order noise; and both against the
+    fp32 formula of model/layers.py:186-197 on the bf16-rounded operands."""
+    from ldt_b200 import ops
+    from ldt_b200.score import _PtrView
+    H, dh, Hd, T = 16, 64, 1024, 32
+    g = torch.Generator().manual_seed(B)
+    M = B * T
+    A = torch.randn((M, Hd), generator=g).to(dev).bfloat16()
+    Wf = (torch.randn((3 * Hd, Hd), generator=g) / Hd ** 0.5)
+    bias = (torch.randn((3 * Hd,), generator=g) * 0.5).to(dev)
+    W = Wf.to(dev).bfloat16().contiguous()
+    perm = torch.stack([torch.arange(H).view(H, 1) * dh + torch.arange(dh).view(1, dh) + off for off in (0, Hd, 2 * Hd)],
+                       dim=1).reshape(-1).to(dev)
+    Wp, bp = W[perm].contiguous(), bias[perm].contiguous()
+    qkv = torch.empty((M, 3 * Hd), dtype=torch.bfloat16, device=dev)
+    o_ref = torch.empty((M, Hd), dtype=torch.bfloat16, device=dev)
+    ops.gemm(A, W, bias, qkv, 1)
+    ops.attention_nk32(B, H, T, dh, qkv, 3 * Hd, _PtrView(qkv.data_ptr() + 2 * Hd), _PtrView(qkv.data_ptr() + 4 * Hd), 3 * Hd, o_ref)
+    o = torch.full((M, Hd), 7.0, dtype=torch.bfloat16, device=dev)
+    ops.qkv_attention(B, H, A, Wp, bp, o)
+    assert rms_rel_err(o.float(), o_ref.float()) < 2e-3, rms_rel_err(o.float(), o_ref.float())
+    # fp32 formula on the bf16-rounded q/k/v
+    q3 = qkv.float()
+    qh = q3[:, :Hd].reshape(B, T, H, dh).permute(0, 2, 1, 3)
+    kh = q3[:, Hd:2 * Hd].reshape(B, T, H, dh).permute(0, 2, 1, 3)
+    vh = q3[:, 2 * Hd:].reshape(B, T, H, dh).permute(0, 2, 1, 3)
+    w = ((qh @ kh.transpose(-2, -1)) * dh ** -0.5).softmax(-1)
+    ref = (w @ vh).reshape(B, T, Hd)   # [B,H,T,dh] buffer re-read token-major (layout quirk)
+    assert rms_rel_err(o.float().view(B, T, Hd), ref) < 4e-3
+    assert rel_rms_err(o.float().view(B, T, Hd), ref) < 3e-2
+
+
 # ------------------------------------------------------------------------------------------------
 # SDE update kernel
 # ------------------------------------------------------------------------------------------------

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--counters", action="store_true", help="print the CTA-pair kernel's stall counters (backend 3)")
     a = ap.parse_args()
+    bench_fused(a.batch, a.reps)
     dev = torch.device("cuda:0")
     M = a.batch * 32
     shapes = [("qkv", 3072, 1024, 1), ("fc_o", 1024, 1024, 3), ("fc1", 4096, 1024, 2), ("fc2", 1024, 4096, 3)]
@@ -71,6 +72,29 @@ def main():
             for k in ks[1:]:
                 d = (outs[k] - outs[ks[0]]).abs().max().item()
                 print(f"   max |backend {k} - backend {ks[0]}| = {d:.3e}")
+
+
+def bench_fused(batch, reps):
+    dev = torch.device("cuda:0")
+    H, dh, Hd = 16, 64, 1024
+    M = batch * 32
+    g = torch.Generator().manual_seed(1)
+    A = torch.randn((M, Hd), generator=g).to(dev).bfloat16()
+    Wp = (torch.randn((3 * Hd, Hd), generator=g) / 32).to(dev).bfloat16()
+    bp = torch.randn((3 * Hd,), generator=g).to(dev)
+    o = torch.empty((M, Hd), dtype=torch.bfloat16, device=dev)
+    for _ in range(5):
+        ops.qkv_attention(batch, H, A, Wp, bp, o)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ops.qkv_attention(batch, H, A, Wp, bp, o)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / reps
+    fl = 2.0 * M * 3 * Hd * Hd + 4.0 * batch * H * 32 * 32 * dh
+    print(f"fused qkv+attention M={M}: {us:8.2f} us  {fl / us / 1e6:8.1f} TFLOP/s", flush=True)
 
 
 if __name__ == "__main__":
