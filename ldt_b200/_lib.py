@@ -46,6 +46,7 @@ PROTOTYPES = {
     "ldt_abi_version": (C.c_int, []),
     "ldt_last_error_string": (C.c_char_p, []),
     "ldt_device_sm_count": (C.c_int, []),
+    "ldt_set_pdl": (C.c_int, [C.c_int]),
     "ldt_nn_distance": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldt_pairwise_cd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,

@@ -1,5 +1,6 @@
 // C-ABI plumbing shared by every entry point: thread-local error string, device attribute cache.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -22,6 +23,8 @@ int check_cuda(cudaError_t e, const char* what, const char* file, int line) {
   return LDT_ERR_CUDA;
 }
 
+void set_pdl(int on);
+
 int num_sms() {
   static int cached = 0;
   if (cached == 0) {
@@ -35,8 +38,22 @@ int num_sms() {
   return cached;
 }
 
+static int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("LDT_PDL");
+    g_pdl = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return g_pdl != 0;
+}
+void set_pdl(int on) { g_pdl = on ? 1 : 0; }
+
 }  // namespace ldt
 
+extern "C" int ldt_set_pdl(int enable) {
+  ldt::set_pdl(enable);
+  return LDT_OK;
+}
 extern "C" int ldt_abi_version(void) { return LDT_ABI_VERSION; }
 extern "C" const char* ldt_last_error_string(void) { return ldt::g_err; }
 extern "C" int ldt_device_sm_count(void) { return ldt::num_sms(); }

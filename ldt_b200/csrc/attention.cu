@@ -26,6 +26,8 @@ attention_nk32_kernel(int units, int H, int Nq, int qtiles, const __nv_bfloat16*
                       __nv_bfloat16* __restrict__ o, float scale_log2e) {
   constexpr int VS = DH + 8;  // padded row (elements): 16-byte aligned rows, conflict-free ldmatrix
   __shared__ __align__(16) __nv_bfloat16 Vs[ATT_WARPS][32 * VS];
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit = blockIdx.x * ATT_WARPS + warp;
   if (unit >= units) return;

@@ -7,6 +7,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <utility>
+
 namespace ldt {
 
 // ---- error plumbing (C-ABI never throws; see include/ldt_b200.h) -------------------------
@@ -36,6 +38,31 @@ enum : int {
 };
 
 int  num_sms();           // cached cudaDevAttrMultiProcessorCount of the current device
+bool pdl_enabled();       // programmatic dependent launch: off by default, on via ldt_set_pdl(1) or env LDT_PDL=1
+
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------
+// Every kernel of the per-step chain starts with pdl_launch_dependents() (the next kernel's CTAs may be scheduled as
+// soon as this grid's CTAs have all started and SM resources free up) and executes pdl_wait() before its first access
+// to global memory (blocks until the preceding grid has completed and flushed).  Net effect: launch latency and the
+// next kernel's prologue (barrier init, TMEM allocation, descriptor prefetch) overlap this kernel's tail.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 
 // ---- small device helpers -------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

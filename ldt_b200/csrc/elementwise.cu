@@ -16,6 +16,8 @@ namespace ldt {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) cast_pad_kernel(long long rows, int cols, const float* __restrict__ in, int ld_in,
                                                      __nv_bfloat16* __restrict__ out, int ld_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int groups = ld_out >> 3;  // 8 outputs (16 bytes) per thread-iteration
   const long long total = rows * groups;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
@@ -56,6 +58,8 @@ __global__ void __launch_bounds__(128) layernorm_mod_kernel(int rows, const floa
                                                           const float* __restrict__ bias, float eps,
                                                           __nv_bfloat16* __restrict__ y) {
   constexpr int C = NV * 128;
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -207,6 +211,8 @@ __global__ void __launch_bounds__(256) sde_step_kernel(long long numel, const fl
                                                      const int* __restrict__ step_index, unsigned long long seed,
                                                      unsigned long long offset, unsigned long long offset_per_step,
                                                      float* __restrict__ x_next, float* __restrict__ x_mean) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int step = step_index ? *step_index : 0;
   const float* c = coef_table + static_cast<size_t>(step) * LDT_SDE_COEF_STRIDE;
   const long long T = static_cast<long long>(gridDim.x) * 256;
@@ -232,10 +238,16 @@ __global__ void __launch_bounds__(256) sde_step_kernel(long long numel, const fl
   }
 }
 
-__global__ void advance_step_kernel(int* step_index) { *step_index += 1; }
+__global__ void advance_step_kernel(int* step_index) {
+  pdl_launch_dependents();
+  pdl_wait();
+  *step_index += 1;
+}
 
 __global__ void __launch_bounds__(256) select_row_kernel(const float* __restrict__ table, long long row_len,
                                                        const int* __restrict__ step_index, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float4* src = reinterpret_cast<const float4*>(table + static_cast<long long>(*step_index) * row_len);
   float4* dst = reinterpret_cast<float4*>(out);
   const long long n4 = row_len >> 2;
@@ -256,9 +268,8 @@ static int cast_pad_impl(const char* who, long long rows, int cols, const float*
               LDT_ERR_INVALID, "%s: null or misaligned pointer", who);
   const long long total = rows * (ld_out / 8);
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(num_sms()) * 16));
-  cast_pad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, cols, in, ld_in,
-                                                                       static_cast<__nv_bfloat16*>(out), ld_out);
-  LDT_CUDA_OK(cudaGetLastError());
+  LDT_CUDA_OK(launch_pdl(cast_pad_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), rows, cols, in, ld_in,
+                         static_cast<__nv_bfloat16*>(out), ld_out));
   return LDT_OK;
 }
 
@@ -285,7 +296,8 @@ extern "C" int ldt_layernorm_mod_bf16(int rows, int C, const float* x, const flo
   const int grid = (rows + 3) / 4;
 #define LDT_LN_CASE(NV)                                                                                              \
   case NV:                                                                                                           \
-    layernorm_mod_kernel<NV><<<grid, 128, 0, s>>>(rows, x, shift, scale, mod_stride, rows_per_mod, weight, bias, eps, yb); \
+    LDT_CUDA_OK(launch_pdl(layernorm_mod_kernel<NV>, dim3(grid), dim3(128), 0, s, rows, x, shift, scale, mod_stride,   \
+                           rows_per_mod, weight, bias, eps, yb));                                                     \
     break
   switch (C / 128) {
     LDT_LN_CASE(1); LDT_LN_CASE(2); LDT_LN_CASE(3); LDT_LN_CASE(4); LDT_LN_CASE(5); LDT_LN_CASE(6); LDT_LN_CASE(7);
@@ -326,8 +338,8 @@ extern "C" int ldt_sde_step(int predictor, long long numel, const float* x, cons
   if (grid <= 0) grid = static_cast<int>(std::min<long long>((numel + 255) / 256, static_cast<long long>(num_sms()) * 8));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define LDT_SDE_LAUNCH(P)                                                                                          \
-  sde_step_kernel<P><<<grid, 256, 0, s>>>(numel, x, params, z, coef_table, step_index, seed, offset, offset_per_step, \
-                                          x_next, x_mean)
+  LDT_CUDA_OK(launch_pdl(sde_step_kernel<P>, dim3(grid), dim3(256), 0, s, numel, x, params, z, coef_table, step_index, \
+                         seed, offset, offset_per_step, x_next, x_mean))
   switch (predictor) {
     case LDT_PRED_ANCESTRAL: LDT_SDE_LAUNCH(LDT_PRED_ANCESTRAL); break;
     case LDT_PRED_REVERSE_DIFFUSION: LDT_SDE_LAUNCH(LDT_PRED_REVERSE_DIFFUSION); break;
@@ -342,8 +354,7 @@ extern "C" int ldt_sde_step(int predictor, long long numel, const float* x, cons
 
 extern "C" int ldt_advance_step(int* step_index, void* stream) {
   LDT_REQUIRE(step_index, LDT_ERR_INVALID, "ldt_advance_step: null pointer");
-  advance_step_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(step_index);
-  LDT_CUDA_OK(cudaGetLastError());
+  LDT_CUDA_OK(launch_pdl(advance_step_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), step_index));
   return LDT_OK;
 }
 
@@ -351,7 +362,7 @@ extern "C" int ldt_select_row(const float* table, long long row_len, const int* 
   LDT_REQUIRE(table && step_index && out && row_len > 0 && row_len % 4 == 0, LDT_ERR_INVALID,
               "ldt_select_row: bad arguments (row_len=%lld must be a multiple of 4)", row_len);
   const int grid = static_cast<int>(std::min<long long>((row_len / 4 + 255) / 256, static_cast<long long>(num_sms()) * 4));
-  select_row_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(table, row_len, step_index, out);
-  LDT_CUDA_OK(cudaGetLastError());
+  LDT_CUDA_OK(launch_pdl(select_row_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), table, row_len,
+                         step_index, out));
   return LDT_OK;
 }

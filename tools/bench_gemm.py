@@ -23,12 +23,15 @@ def main():
     ap.add_argument("--backends", default="2,3")
     ap.add_argument("--reps", type=int, default=50)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--extra", action="store_true")
     ap.add_argument("--counters", action="store_true", help="print the CTA-pair kernel's stall counters (backend 3)")
     a = ap.parse_args()
     bench_fused(a.batch, a.reps)
     dev = torch.device("cuda:0")
     M = a.batch * 32
     shapes = [("qkv", 3072, 1024, 1), ("fc_o", 1024, 1024, 3), ("fc1", 4096, 1024, 2), ("fc2", 1024, 4096, 3)]
+    if a.extra:
+        shapes = [("fc1/bias-only", 4096, 1024, 1), ("fc1/gelu", 4096, 1024, 2), ("fc1/f32", 4096, 1024, 0)]
     g = torch.Generator().manual_seed(0)
     for name, N, K, epi in shapes:
         A = (torch.randn((M, K), generator=g) * 0.5).to(dev).bfloat16()
