@@ -300,7 +300,14 @@ def main():
         gemm_ms, gemm_flop = prof["gemm_ms"], prof["gemm_flop"]
         achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12
         step_flop = B * (N * FLOP_SCORE_PER_SAMPLE_STEP + FLOP_DECODE_PER_CLOUD)
-        roof = {"bound": "tensor", "achieved": achieved, "peak": sus, "unit": "TFLOP/s", "frac": achieved / sus, "traffic": None,
+        traffic = None
+        try:   # per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture (profiles/)
+            import glob
+            tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic*.json")))[-1]
+            traffic = json.load(open(tf))["gemm_tc2_kernel"]["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        roof = {"bound": "tensor", "achieved": achieved, "peak": sus, "unit": "TFLOP/s", "frac": achieved / sus, "traffic": traffic,
                 "kernel": "gemm_tc2_kernel + qkv_attention_kernel (tcgen05.mma.cta_group::2 256-row tiles, TMEM accumulators, TMA-fed)", "peak_source": src + ", sustained figure",
                 "launches_timed": prof["gemm_launches"], "gemm_share_of_step": prof["gemm_ms"] / prof["total_ms"],
                 "whole_step_achieved": step_flop * args.steps / t_dev / 1e12,

@@ -266,19 +266,19 @@ __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f +
 // below fp32 resolution of 1+erf and 3 orders below the bf16 rounding applied to the result), 2 MUFU + 11 FP32 ops
 // instead of erff's two divergent branches.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = x * 0.70710678118654752440f;
-  const float az = fabsf(z);
+  // z = x / sqrt(2) never materialises: |z| enters through pre-scaled constants, and the sign through |x/2|:
+  //   gelu(x) = x/2 + |x/2| * erf(|z|)       (erf odd)
   float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.0f)));
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   poly *= t;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(az * az * -1.4426950408889634f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((x * x) * (-0.5f * 1.4426950408889634f)));
   const float erf_abs = fmaf(-poly, e, 1.0f);
   const float hx = 0.5f * x;
-  return fmaf(hx, copysignf(erf_abs, z), hx);
+  return fmaf(fabsf(hx), erf_abs, hx);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);

@@ -123,73 +123,88 @@ __device__ __forceinline__ void epilogue_row32(const EpiParams& p, int row, int 
 // ------------------------------------------------------------------------------------------------
 constexpr int EPI_STG_BYTES = 4096;  // per warp
 
-template <int EPI>
+template <int EPI, int NCOLS, typename WaitFn>
 __device__ __forceinline__ void epilogue_staged(const EpiParams& p, uint8_t* stg, int lane, int row_base, int col_base,
-                                                int ncols, uint32_t taddr) {
+                                                uint32_t taddr, WaitFn wait_accumulator) {
+  constexpr int ncols = NCOLS;
   const uint32_t stg_u32 = smem_u32(stg);
   const uint32_t st_row = stg_u32 + static_cast<uint32_t>(lane) * 128u;   // staging row written by this lane
   const int rr0 = lane >> 3, cc = lane & 7;                                // read-back: row rr0 + 4*i, chunk cc
   if constexpr (EPI == LDT_EPI_BIAS_F32 || EPI == LDT_EPI_GATE_RESID_F32) {
+    constexpr int NU = NCOLS / 32;
     // one gate row for the whole 32-row slab (rows_per_gate a multiple of 32, e.g. the 32 latent tokens of a sample)?
     const bool gate_uniform = (p.rows_per_gate & 31) == 0 && (row_base & 31) == 0;
-#pragma unroll 1
-    for (int c0 = 0; c0 < ncols; c0 += 32) {
-      if (col_base + c0 >= p.N) break;
+    // Residual rows are software-pipelined one unit ahead (and unit 0 is fetched BEFORE the accumulator is waited
+    // for): they do not depend on the MMA, and with <= 1 KB of L1 left beside 225 KB of shared memory every one of
+    // them is an L2 round trip.  out may alias resid element for element; a unit's loads precede its stores.
+    float4 r4[2][8];
+    auto fetch_resid = [&](int u, float4(&r)[8]) {
+      const int col = col_base + u * 32 + cc * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = row_base + rr0 + 4 * i;
+        r[i] = (col < p.N && row < p.M)
+                   ? __ldcg(reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(row) * p.ldo + col))
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if constexpr (EPI == LDT_EPI_GATE_RESID_F32) fetch_resid(0, r4[0]);
+    wait_accumulator();
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const int c0 = u * 32;
       const int col = col_base + c0 + cc * 4;
       const bool col_ok = col < p.N;   // N % 8 == 0 and col % 4 == 0: the whole float4 is inside
-      // residual / gate / bias first: independent of the accumulator, so their latency hides behind the TMEM drain.
-      // (out may alias resid element for element; all loads of a unit are issued before its first store.)
-      float4 r4[8];
+      if constexpr (EPI == LDT_EPI_GATE_RESID_F32) {
+        if (u + 1 < NU) fetch_resid(u + 1, r4[(u + 1) & 1]);
+      }
       float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if constexpr (EPI == LDT_EPI_GATE_RESID_F32) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = row_base + rr0 + 4 * i;
-          r4[i] = (col_ok && row < p.M)
-                      ? __ldcg(reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(row) * p.ldo + col))
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
         if (col_ok && p.gate != nullptr && gate_uniform)
           g4 = __ldg(reinterpret_cast<const float4*>(
               p.gate + static_cast<long long>(row_base / p.rows_per_gate) * p.gate_stride + col));
       }
       if (col_ok && p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-      uint32_t v[32];
-      tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), v);
-      tmem_ld_wait();
+      if (col_base + c0 < p.N) {   // warp-uniform: this unit has at least one live column
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint32_t a = st_row + static_cast<uint32_t>((c ^ (lane & 7)) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * c]), "r"(v[4 * c + 1]),
-                     "r"(v[4 * c + 2]), "r"(v[4 * c + 3])
-                     : "memory");
-      }
-      __syncwarp();
-      if (col_ok) {
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t a = st_row + static_cast<uint32_t>((c ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * c]), "r"(v[4 * c + 1]),
+                       "r"(v[4 * c + 2]), "r"(v[4 * c + 3])
+                       : "memory");
+        }
+        __syncwarp();
+        if (col_ok) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = rr0 + 4 * i;
-          const int row = row_base + rr;
-          float4 a4;
-          const uint32_t a = stg_u32 + static_cast<uint32_t>(rr * 128 + ((cc ^ (rr & 7)) << 4));
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w) : "r"(a));
-          if (row < p.M) {
-            a4.x += b4.x; a4.y += b4.y; a4.z += b4.z; a4.w += b4.w;
-            if constexpr (EPI == LDT_EPI_GATE_RESID_F32) {
-              float4 g = g4;
-              if (p.gate != nullptr && !gate_uniform)
-                g = __ldg(reinterpret_cast<const float4*>(
-                    p.gate + static_cast<long long>(row / p.rows_per_gate) * p.gate_stride + col));
-              a4.x = r4[i].x + g.x * a4.x; a4.y = r4[i].y + g.y * a4.y;
-              a4.z = r4[i].z + g.z * a4.z; a4.w = r4[i].w + g.w * a4.w;
+          for (int i = 0; i < 8; ++i) {
+            const int rr = rr0 + 4 * i;
+            const int row = row_base + rr;
+            float4 a4;
+            const uint32_t a = stg_u32 + static_cast<uint32_t>(rr * 128 + ((cc ^ (rr & 7)) << 4));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w) : "r"(a));
+            if (row < p.M) {
+              a4.x += b4.x; a4.y += b4.y; a4.z += b4.z; a4.w += b4.w;
+              if constexpr (EPI == LDT_EPI_GATE_RESID_F32) {
+                float4 g = g4;
+                if (p.gate != nullptr && !gate_uniform)
+                  g = __ldg(reinterpret_cast<const float4*>(
+                      p.gate + static_cast<long long>(row / p.rows_per_gate) * p.gate_stride + col));
+                const float4 r = r4[u & 1][i];
+                a4.x = r.x + g.x * a4.x; a4.y = r.y + g.y * a4.y;
+                a4.z = r.z + g.z * a4.z; a4.w = r.w + g.w * a4.w;
+              }
+              *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col) = a4;
             }
-            *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col) = a4;
           }
         }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
+    wait_accumulator();
 #pragma unroll 1
     for (int c0 = 0; c0 < ncols; c0 += 64) {
       if (col_base + c0 >= p.N) break;
@@ -538,15 +553,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m0 = (tile % tiles_m) * T2_BM + static_cast<int>(rank) * 128;
       const int n0 = (tile / tiles_m) * BN;
-      const long long w0 = clock64();
-      mbar_wait(&tfull[acc], acc_phase);
-      t_tfull += clock64() - w0;
-      tc_fence_after();
       {
         const int col = half * (BN / 2);
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * Cfg::ACC_STRIDE + col);
-        epilogue_staged<EPI>(p, stg, lane, m0 + quad * 32, n0 + col, BN / 2, taddr);
+        epilogue_staged<EPI, BN / 2>(p, stg, lane, m0 + quad * 32, n0 + col, taddr, [&]() {
+          const long long w0 = clock64();
+          mbar_wait(&tfull[acc], acc_phase);
+          t_tfull += clock64() - w0;
+          tc_fence_after();
+        });
       }
       tc_fence_before();
       __syncwarp();

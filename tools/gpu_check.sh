@@ -23,10 +23,12 @@ for st in $STAGES; do
     benchref) run benchref 600 python bench.py --impl reference --steps 1 --warmup 0 ;;
     launches) run launches 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --sde-steps 2 --steps 1 --warmup 1 --no-cpu-baseline --cd-clouds 16 ;;
     ncufull)
-      for k in gemm_tc_kernel layernorm_mod_kernel attention_nk32_kernel pairwise_cd_kernel sde_step_kernel; do
+      for k in ${NCU_KERNELS:-gemm_tc2_kernel qkv_attention_kernel layernorm_mod_kernel sde_step_kernel}; do
         run ncu_$k 400 ncu --set full --clock-control none --import-source on -k regex:$k -s ${NCU_SKIP:-6} -c 2 -f -o gpurun_out/prof_$k \
           python bench.py --sde-steps 2 --steps 1 --warmup 1 --no-cpu-baseline --cd-clouds 16
       done ;;
+    ncucd) run ncu_pairwise_cd 400 ncu --set full --clock-control none --import-source on -k regex:pairwise_cd_kernel -c 1 -f -o gpurun_out/prof_pairwise_cd_kernel \
+          python bench.py --sde-steps 2 --steps 1 --warmup 1 --no-cpu-baseline --cd-clouds 64 ;;
     *) echo "unknown stage $st" ;;
   esac
 done
