@@ -105,17 +105,21 @@ __global__ void __launch_bounds__(CD_THREADS) pairwise_cd_kernel(int nb, int pa,
                                                                 int ncols_out, int col_begin,
                                                                 float* __restrict__ out) {
   extern __shared__ float4 cd_smem[];
-  float4* cand = cd_smem;                                        // [pb]
-  unsigned* colmin = reinterpret_cast<unsigned*>(cand + pb);     // [pb]
+  const int pb32 = (pb + 31) & ~31;                              // candidates padded to whole groups of 32
+  float4* cand = cd_smem;                                        // [pb32]
+  unsigned* colmin = reinterpret_cast<unsigned*>(cand + pb32);   // [pb32]
   __shared__ double red[2][CD_THREADS / 32];
 
   const int i = row_begin + blockIdx.y;
   const int j = col_begin + blockIdx.x;
   const float* a = A + static_cast<size_t>(i) * pa * 3;
   const float* b = B + static_cast<size_t>(j) * pb * 3;
+  const int lane = threadIdx.x & 31;
 
-  for (int k = threadIdx.x; k < pb; k += CD_THREADS) {
-    cand[k] = make_float4(b[k * 3 + 0], b[k * 3 + 1], b[k * 3 + 2], 0.f);
+  const float inf = __int_as_float(0x7f800000);
+  for (int k = threadIdx.x; k < pb32; k += CD_THREADS) {
+    // padding candidates sit at +inf: their distance to anything is +inf, so they never win a minimum
+    cand[k] = (k < pb) ? make_float4(b[k * 3 + 0], b[k * 3 + 1], b[k * 3 + 2], 0.f) : make_float4(inf, inf, inf, 0.f);
     colmin[k] = 0x7f800000u;  // +inf
   }
   __syncthreads();
@@ -133,20 +137,37 @@ __global__ void __launch_bounds__(CD_THREADS) pairwise_cd_kernel(int nb, int pa,
       qx[u] = a[pc * 3 + 0];
       qy[u] = a[pc * 3 + 1];
       qz[u] = a[pc * 3 + 2];
-      best[u] = __int_as_float(0x7f800000);
+      best[u] = inf;
     }
-#pragma unroll 2
-    for (int k = 0; k < pb; ++k) {
-      const float4 p = cand[k];
-      float cm = __int_as_float(0x7f800000);
+    // Candidates go two at a time so that every running minimum is a 3-input FMNMX3 (min of the old value and two
+    // new distances): 0.5 min instructions per point pair for the row minima and 0.5 for the column minima, on top of
+    // the 6 FP32 operations of the distance itself.  The warp-wide column minimum (REDUX) of candidate k0+j is parked
+    // in lane j; one shared-memory atomicMin per 32 candidates publishes them (4 per-candidate bookkeeping
+    // instructions instead of a per-candidate atomic).
+    for (int k0 = 0; k0 < pb32; k0 += 32) {
+      unsigned mycol = 0x7f800000u;
 #pragma unroll
-      for (int u = 0; u < CD_QPT; ++u) {
-        const float d = sqdist_ref(p.x - qx[u], p.y - qy[u], p.z - qz[u]);
-        best[u] = fminf(best[u], d);
-        cm = fminf(cm, d);
+      for (int jj = 0; jj < 32; jj += 2) {
+        const float4 p0 = cand[k0 + jj];
+        const float4 p1 = cand[k0 + jj + 1];
+        float cm0 = inf, cm1 = inf;
+#pragma unroll
+        for (int u = 0; u < CD_QPT; u += 2) {
+          const float d00 = sqdist_ref(p0.x - qx[u], p0.y - qy[u], p0.z - qz[u]);
+          const float d01 = sqdist_ref(p0.x - qx[u + 1], p0.y - qy[u + 1], p0.z - qz[u + 1]);
+          const float d10 = sqdist_ref(p1.x - qx[u], p1.y - qy[u], p1.z - qz[u]);
+          const float d11 = sqdist_ref(p1.x - qx[u + 1], p1.y - qy[u + 1], p1.z - qz[u + 1]);
+          best[u] = fminf(fminf(best[u], d00), d10);
+          best[u + 1] = fminf(fminf(best[u + 1], d01), d11);
+          cm0 = fminf(fminf(cm0, d00), d01);
+          cm1 = fminf(fminf(cm1, d10), d11);
+        }
+        const unsigned w0 = __reduce_min_sync(0xffffffffu, __float_as_uint(cm0));
+        const unsigned w1 = __reduce_min_sync(0xffffffffu, __float_as_uint(cm1));
+        if (lane == jj) mycol = w0;
+        if (lane == jj + 1) mycol = w1;
       }
-      const unsigned wm = __reduce_min_sync(0xffffffffu, __float_as_uint(cm));
-      if ((threadIdx.x & 31) == 0) atomicMin(&colmin[k], wm);
+      atomicMin(&colmin[k0 + lane], mycol);
     }
 #pragma unroll
     for (int u = 0; u < CD_QPT; ++u)
@@ -212,7 +233,7 @@ extern "C" int ldt_pairwise_cd(int na, int nb, int pa, int pb, const float* a, c
   const int rows = row_end - row_begin;
   if (rows == 0 || nb == 0) return LDT_OK;
   LDT_REQUIRE(a && b && out, LDT_ERR_INVALID, "ldt_pairwise_cd: null pointer");
-  const size_t smem = static_cast<size_t>(pb) * (sizeof(float4) + sizeof(unsigned));
+  const size_t smem = static_cast<size_t>((pb + 31) & ~31) * (sizeof(float4) + sizeof(unsigned));
   LDT_REQUIRE(smem <= 200 * 1024, LDT_ERR_UNSUPPORTED, "ldt_pairwise_cd: pb=%d needs %zu B of shared memory", pb, smem);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   static bool attr_set = false;
