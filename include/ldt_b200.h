@@ -55,6 +55,23 @@ int ldt_nn_distance(int b, int n, const float* xyz1, int m, const float* xyz2, f
 int ldt_pairwise_cd(int na, int nb, int pa, int pb, const float* a, const float* b, int row_begin, int row_end,
                     float* out, void* stream);
 
+/* Approximate earth-mover distance (forward only).  Replaces approxmatch() + matchcost()
+ * (evaluation/pytorch_structural_losses/src/approxmatch.cu:299-316), bound as StructuralLossesBackend.ApproxMatch /
+ * MatchCost (src/structural_loss.cpp:14-78) and used through StructuralLosses.match_cost (match_cost.py:6-45).
+ *   xyz1 [b,n,3] f32, xyz2 [b,m,3] f32; n, m <= 4096.
+ * ldt_match_cost          cost [b]  = MatchCost(xyz1, xyz2, ApproxMatch(xyz1, xyz2)) without materialising the match
+ * ldt_approx_match        match [b,m,n] f32 (dense; the caller provides b*m*n floats), as ApproxMatch returns it
+ * ldt_match_cost_from_match  cost [b] from a given match, as MatchCost
+ * ldt_pairwise_emd        rows [row_begin,row_end) of out[i,j] = match_cost(a_i, b_j) / p -- what _pairwise_EMD_CD_
+ *                         (evaluation/evaluation_metrics.py:112-162) assembles with one kernel-launch pair per
+ *                         (row, column batch); a [na,p,3], b [nb,p,3], out [(row_end-row_begin), nb] row-major. */
+int ldt_match_cost(int b, int n, int m, const float* xyz1, const float* xyz2, float* cost, void* stream);
+int ldt_approx_match(int b, int n, int m, const float* xyz1, const float* xyz2, float* match, void* stream);
+int ldt_match_cost_from_match(int b, int n, int m, const float* xyz1, const float* xyz2, const float* match, float* cost,
+                              void* stream);
+int ldt_pairwise_emd(int na, int nb, int p, const float* a, const float* b, int row_begin, int row_end, float* out,
+                     void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Dense contraction core (used by the score net and the decoder; exported for parity tests)
  *   C[M,N] = epilogue( A[M,K] . W[N,K]^T + bias[N] )

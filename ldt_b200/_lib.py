@@ -51,6 +51,12 @@ PROTOTYPES = {
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldt_pairwise_cd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p]),
+    "ldt_match_cost": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldt_approx_match": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldt_match_cost_from_match": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p]),
+    "ldt_pairwise_emd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_void_p]),
     "ldt_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "ldt_debug_set_gemm_counters": (C.c_int, [C.c_void_p]),
     "ldt_cast_pad_bf16": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),

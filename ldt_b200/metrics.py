@@ -1,9 +1,14 @@
-"""Generation metrics on the Chamfer matrix -- host mirror of reference evaluation/evaluation_metrics.py.
+"""Generation metrics on pairwise cloud-distance matrices -- host mirror of reference
+evaluation/evaluation_metrics.py (same function names, arguments and result keys).
 
-``_pairwise_CD_`` (:165-198) becomes ONE kernel launch per matrix (``ldt_pairwise_cd``) instead of
-2*N*ceil(N/batch) launches plus expand/mean/cat; ``lgan_mmd_cov`` (:234-246) and ``knn`` (:202-231) are
-O(N^2) bookkeeping on the finished matrices and stay in torch, with the reference's exact op sequence so
-cloud-level argmins agree.  ``batch_size`` is accepted for signature compatibility and ignored.
+What changes underneath:
+* ``_pairwise_CD_`` (:165-198) and ``_pairwise_EMD_CD_`` (:112-162) loop in Python over every row cloud and every
+  column batch (2 kernel launches + expand/contiguous/mean/cat per iteration); here a whole matrix is ONE launch of
+  ``ldt_pairwise_cd`` / ``ldt_pairwise_emd``.  ``batch_size`` and the ``accelerated_*`` flags are accepted for signature
+  compatibility and ignored (there is only the CUDA path).
+* ``lgan_mmd_cov`` (:234-246) and ``knn`` (:202-231) are O(N^2) bookkeeping on finished matrices and stay in torch;
+  they are written so that every reduction the reference takes (column/row minima, first-occurrence argmin, the 1-NN
+  vote) sees identical inputs and therefore returns identical numbers.
 """
 from __future__ import annotations
 
@@ -18,52 +23,96 @@ def distChamferCUDA(x, y):
     return d1, d2
 
 
+def emd_approx_cuda(sample, ref):
+    """Approximate EMD per pair, divided by the point count (:39-45)."""
+    B, N, N_ref = sample.size(0), sample.size(1), ref.size(1)
+    assert N == N_ref, "Not sure what would EMD do in this case"
+    return ops.match_cost(sample.contiguous(), ref.contiguous()) / float(N)
+
+
+def _rows(rows, n):
+    return (0, n) if rows is None else rows
+
+
 def _pairwise_CD_(sample_pcs, ref_pcs, batch_size=None, verbose=True, rows=None):
     """[N_sample, N_ref] matrix, entry (i, j) = CD(sample i, ref j).  ``rows=(begin, end)`` computes a row block
     (used to shard the matrix over GPUs)."""
     a = sample_pcs.contiguous().float()
     b = ref_pcs.contiguous().float()
-    begin, end = (0, a.shape[0]) if rows is None else rows
+    begin, end = _rows(rows, a.shape[0])
     return ops.pairwise_cd(a, b, begin, end)
 
 
+def _pairwise_EMD_CD_(sample_pcs, ref_pcs, batch_size=None, accelerated_cd=True, accelerated_emd=True, rows=None):
+    """(CD matrix, EMD matrix), both [N_sample, N_ref]."""
+    a = sample_pcs.contiguous().float()
+    b = ref_pcs.contiguous().float()
+    begin, end = _rows(rows, a.shape[0])
+    return ops.pairwise_cd(a, b, begin, end), ops.pairwise_emd(a, b, begin, end)
+
+
 def knn(Mxx, Mxy, Myy, k, sqrt=False):
-    """1-NN two-sample test (:202-231)."""
-    n0 = Mxx.size(0)
-    n1 = Myy.size(0)
-    label = torch.cat((torch.ones(n0), torch.zeros(n1))).to(Mxx)
-    M = torch.cat((torch.cat((Mxx, Mxy), 1), torch.cat((Mxy.transpose(0, 1), Myy), 1)), 0)
+    """1-NN two-sample test (:202-231): leave-one-out k-NN classification of the union of both sets."""
+    n0, n1 = Mxx.size(0), Myy.size(0)
+    n = n0 + n1
+    dist = torch.cat([torch.cat([Mxx, Mxy], dim=1), torch.cat([Mxy.t(), Myy], dim=1)], dim=0)
     if sqrt:
-        M = M.abs().sqrt()
-    INFINITY = float("inf")
-    val, idx = (M + torch.diag(INFINITY * torch.ones(n0 + n1).to(Mxx))).topk(k, 0, False)
-    count = torch.zeros(n0 + n1).to(Mxx)
-    for i in range(0, k):
-        count = count + label.index_select(0, idx[i])
-    pred = torch.ge(count, (float(k) / 2) * torch.ones(n0 + n1).to(Mxx)).float()
-    s = {
+        dist = dist.abs().sqrt()
+    dist = dist + torch.diag(torch.full((n,), float("inf"), device=dist.device, dtype=dist.dtype))  # exclude self
+    nearest = dist.topk(k, dim=0, largest=False).indices                      # [k, n]
+    label = (torch.arange(n, device=dist.device) < n0).to(Mxx.dtype)          # 1 = first set
+    votes = label[nearest].sum(dim=0)
+    pred = (votes >= k / 2.0).to(Mxx.dtype)
+    stats = {
         "tp": (pred * label).sum(),
         "fp": (pred * (1 - label)).sum(),
         "fn": ((1 - pred) * label).sum(),
         "tn": ((1 - pred) * (1 - label)).sum(),
     }
-    s.update({
-        "precision": s["tp"] / (s["tp"] + s["fp"] + 1e-10),
-        "recall": s["tp"] / (s["tp"] + s["fn"] + 1e-10),
-        "acc": torch.eq(label, pred).float().mean(),
-    })
-    return s
+    stats["precision"] = stats["tp"] / (stats["tp"] + stats["fp"] + 1e-10)
+    stats["recall"] = stats["tp"] / (stats["tp"] + stats["fn"] + 1e-10)
+    stats["acc"] = (label == pred).to(Mxx.dtype).mean()
+    return stats
 
 
 def lgan_mmd_cov(all_dist):
     """MMD / COV from an [N_sample, N_ref] distance matrix (:234-246)."""
-    N_sample, N_ref = all_dist.size(0), all_dist.size(1)
-    min_val_fromsmp, min_idx = torch.min(all_dist, dim=1)
-    min_val, _ = torch.min(all_dist, dim=0)
-    mmd = min_val.mean()
-    cov = float(min_idx.unique().view(-1).size(0)) / float(N_ref)
-    cov = torch.tensor(cov).to(all_dist)
+    n_ref = all_dist.size(1)
+    covered = all_dist.argmin(dim=1)               # which reference cloud each sample is closest to
+    mmd = all_dist.min(dim=0).values.mean()        # every reference cloud's distance to its closest sample
+    cov = torch.tensor(covered.unique().numel() / float(n_ref)).to(all_dist)
     return {"mmd": mmd, "cov": cov}
+
+
+def _update(results, res, suffix, only_acc=False):
+    for k, v in res.items():
+        if only_acc and "acc" not in k:
+            continue
+        results[("1-NN-%s-%s" % (suffix, k)) if only_acc else ("%s-%s" % (k, suffix))] = v
+
+
+def compute_all_metrics(sample_pcs, ref_pcs, batch_size=None, accelerated_cd=True, accelerated_emd=True):
+    """MMD / COV / 1-NNA for both CD and approximate EMD (:249-277)."""
+    results = {}
+    ref_pcs, sample_pcs = ref_pcs.cuda(), sample_pcs.cuda()
+    M_rs_cd, M_rs_emd = _pairwise_EMD_CD_(ref_pcs, sample_pcs, batch_size)
+    _update(results, lgan_mmd_cov(M_rs_cd.t()), "CD")
+    _update(results, lgan_mmd_cov(M_rs_emd.t()), "EMD")
+    M_rr_cd, M_rr_emd = _pairwise_EMD_CD_(ref_pcs, ref_pcs, batch_size)
+    M_ss_cd, M_ss_emd = _pairwise_EMD_CD_(sample_pcs, sample_pcs, batch_size)
+    _update(results, knn(M_rr_cd, M_rs_cd, M_ss_cd, 1, sqrt=False), "CD", only_acc=True)
+    _update(results, knn(M_rr_emd, M_rs_emd, M_ss_emd, 1, sqrt=False), "EMD", only_acc=True)
+    return results
+
+
+def compute_MMD_metrics(sample_pcs, ref_pcs, batch_size=None, accelerated_cd=True, accelerated_emd=True):
+    """MMD / COV for CD and EMD only (:280-296)."""
+    results = {}
+    ref_pcs, sample_pcs = ref_pcs.cuda(), sample_pcs.cuda()
+    M_rs_cd, M_rs_emd = _pairwise_EMD_CD_(ref_pcs, sample_pcs, batch_size)
+    _update(results, lgan_mmd_cov(M_rs_cd.t()), "CD")
+    _update(results, lgan_mmd_cov(M_rs_emd.t()), "EMD")
+    return results
 
 
 def compute_CD_metrics(sample_pcs, ref_pcs, batch_size=None):
@@ -71,10 +120,8 @@ def compute_CD_metrics(sample_pcs, ref_pcs, batch_size=None):
     results = {}
     ref_pcs, sample_pcs = ref_pcs.cuda(), sample_pcs.cuda()
     M_rs_cd = _pairwise_CD_(ref_pcs, sample_pcs, batch_size)
-    res_cd = lgan_mmd_cov(M_rs_cd.t())
-    results.update({"%s-CD" % k: v for k, v in res_cd.items()})
+    _update(results, lgan_mmd_cov(M_rs_cd.t()), "CD")
     M_rr_cd = _pairwise_CD_(ref_pcs, ref_pcs, batch_size)
     M_ss_cd = _pairwise_CD_(sample_pcs, sample_pcs, batch_size)
-    one_nn_cd_res = knn(M_rr_cd, M_rs_cd, M_ss_cd, 1, sqrt=False)
-    results.update({"1-NN-CD-%s" % k: v for k, v in one_nn_cd_res.items() if "acc" in k})
+    _update(results, knn(M_rr_cd, M_rs_cd, M_ss_cd, 1, sqrt=False), "CD", only_acc=True)
     return results

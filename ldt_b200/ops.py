@@ -103,6 +103,58 @@ def pairwise_cd(a: torch.Tensor, b: torch.Tensor, row_begin: int = 0, row_end: i
     return out
 
 
+def _check_sets(a, b, who):
+    _req(a, torch.float32, "set_d")
+    _req(b, torch.float32, "set_q")
+    if a.dim() != 3 or b.dim() != 3 or a.shape[2] != 3 or b.shape[2] != 3 or a.shape[0] != b.shape[0]:
+        raise RuntimeError(f"{who}: expected [b,n,3] and [b,m,3], got {tuple(a.shape)} and {tuple(b.shape)}")
+
+
+def match_cost(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """cost [b] of the approximate EMD matching (StructuralLosses.match_cost forward), match never materialised."""
+    _check_sets(a, b, "match_cost")
+    cost = torch.empty((a.shape[0],), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device), _launch("match_cost"):
+        check(load().ldt_match_cost(a.shape[0], a.shape[1], b.shape[1], ptr(a), ptr(b), ptr(cost), stream_ptr()),
+              "ldt_match_cost")
+    return cost
+
+
+def approx_match(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Dense match [b,m,n] as StructuralLossesBackend.ApproxMatch returns it (structural_loss.cpp:14-44)."""
+    _check_sets(a, b, "approx_match")
+    match = torch.empty((a.shape[0], b.shape[1], a.shape[1]), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device), _launch("approx_match"):
+        check(load().ldt_approx_match(a.shape[0], a.shape[1], b.shape[1], ptr(a), ptr(b), ptr(match), stream_ptr()),
+              "ldt_approx_match")
+    return match
+
+
+def match_cost_from_match(a: torch.Tensor, b: torch.Tensor, match: torch.Tensor) -> torch.Tensor:
+    """StructuralLossesBackend.MatchCost (structural_loss.cpp:46-78)."""
+    _check_sets(a, b, "match_cost_from_match")
+    _req(match, torch.float32, "match")
+    cost = torch.empty((a.shape[0],), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device), _launch("match_cost_from_match"):
+        check(load().ldt_match_cost_from_match(a.shape[0], a.shape[1], b.shape[1], ptr(a), ptr(b), ptr(match), ptr(cost),
+                                               stream_ptr()), "ldt_match_cost_from_match")
+    return cost
+
+
+def pairwise_emd(a: torch.Tensor, b: torch.Tensor, row_begin: int = 0, row_end: int | None = None) -> torch.Tensor:
+    """Rows [row_begin,row_end) of the [na,nb] approximate-EMD matrix (match cost / points) between cloud sets."""
+    _req(a, torch.float32, "a")
+    _req(b, torch.float32, "b")
+    if a.dim() != 3 or b.dim() != 3 or a.shape[2] != 3 or b.shape[2] != 3 or a.shape[1] != b.shape[1]:
+        raise RuntimeError(f"expected [na,p,3] and [nb,p,3] with equal point counts, got {tuple(a.shape)} and {tuple(b.shape)}")
+    row_end = a.shape[0] if row_end is None else row_end
+    out = torch.empty((row_end - row_begin, b.shape[0]), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device), _launch("pairwise_emd"):
+        check(load().ldt_pairwise_emd(a.shape[0], b.shape[0], a.shape[1], ptr(a), ptr(b), row_begin, row_end, ptr(out),
+                                      stream_ptr()), "ldt_pairwise_emd")
+    return out
+
+
 def gemm(A: torch.Tensor, W: torch.Tensor, bias, out: torch.Tensor, epilogue: int, *, N: int | None = None,
          K: int | None = None, resid=None, gate=None, gate_stride: int = 0, rows_per_gate: int = 1,
          backend: int = 0) -> torch.Tensor:

@@ -144,6 +144,70 @@ def test_cd_metrics_match_reference_golden(dev):
 
 
 # ------------------------------------------------------------------------------------------------
+# approximate EMD (ApproxMatch + MatchCost forward)
+# ------------------------------------------------------------------------------------------------
+def _ref_emd(dev, a, b):
+    """The reference's own approxmatch/matchcost kernels (compiled from its source into oracle/_ref) on this GPU."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_emd.so")
+    assert os.path.exists(path), "oracle/_ref/libref_emd.so missing: run `make -C oracle` in the build container"
+    R = C.CDLL(path)
+    am = getattr(R, "_Z11approxmatchiiiPKfS0_PfS1_P11CUstream_st")   # approxmatch(...), approxmatch.cu:299
+    mc = getattr(R, "_Z9matchcostiiiPKfS0_PfS1_P11CUstream_st")      # matchcost(...),   approxmatch.cu:309
+    am.argtypes = [C.c_int] * 3 + [C.c_void_p] * 5
+    mc.argtypes = [C.c_int] * 3 + [C.c_void_p] * 5
+    bs, n, m = a.shape[0], a.shape[1], b.shape[1]
+    match = torch.zeros((bs, m, n), device=dev)
+    temp = torch.zeros((bs, (n + m) * 2), device=dev)
+    cost = torch.zeros((bs,), device=dev)
+    torch.cuda.synchronize()
+    am(bs, n, m, a.data_ptr(), b.data_ptr(), match.data_ptr(), temp.data_ptr(), None)
+    mc(bs, n, m, a.data_ptr(), b.data_ptr(), match.data_ptr(), cost.data_ptr(), None)
+    torch.cuda.synchronize()
+    return match, cost
+
+
+@pytest.mark.parametrize("bs,n,m", [(3, 256, 256), (2, 2048, 2048), (33, 100, 100), (2, 512, 256), (2, 300, 900), (1, 1, 1)])
+def test_match_cost_vs_reference_cuda_kernels(dev, bs, n, m):
+    """Fused match cost (no dense match) and the materialised match against the reference kernels on the same inputs.
+    Tolerance: the fused kernel sums w*d per level instead of (sum of w)*d per entry -> fp32 association differences."""
+    from ldt_b200 import ops
+    g = torch.Generator().manual_seed(bs * 1000 + n + m)
+    a = (torch.rand((bs, n, 3), generator=g) - 0.5).to(dev)
+    b = (torch.rand((bs, m, 3), generator=g) - 0.5).to(dev) * 0.9
+    ref_match, ref_cost = _ref_emd(dev, a, b)
+    cost = ops.match_cost(a, b)
+    assert torch.allclose(cost, ref_cost, rtol=5e-5, atol=1e-6), (cost, ref_cost)
+    match = ops.approx_match(a, b)
+    assert torch.allclose(match, ref_match, rtol=1e-4, atol=1e-7), (match - ref_match).abs().max()
+    cost2 = ops.match_cost_from_match(a, b, match)
+    assert torch.allclose(cost2, ref_cost, rtol=5e-5, atol=1e-6)
+
+
+def test_match_cost_vs_cpu_oracle_and_pairwise_matrix(dev):
+    from ldt_b200 import metrics, ops
+    L = C.CDLL(os.path.join(ROOT, "oracle", "liboracle_emd.so"))
+    L.oracle_match_cost.argtypes = [C.c_int] * 3 + [C.c_void_p] * 4
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn((4, 128, 3), generator=g) * 0.3
+    b = torch.randn((4, 128, 3), generator=g) * 0.3
+    want = torch.empty(4)
+    L.oracle_match_cost(4, 128, 128, a.data_ptr(), b.data_ptr(), want.data_ptr(), None)
+    got = ops.match_cost(a.to(dev), b.to(dev)).cpu()
+    assert torch.allclose(got, want, rtol=2e-4, atol=1e-6), (got, want)   # CPU expf vs GPU ex2.approx
+    # matrix form == per-pair match cost / points, rows sharded or not
+    M = ops.pairwise_emd(a.to(dev), b.to(dev))
+    for i in range(4):
+        row = ops.match_cost(a[i:i + 1].expand(4, -1, -1).contiguous().to(dev), b.to(dev)) / 128.0
+        assert torch.equal(M[i], row)
+    assert torch.equal(ops.pairwise_emd(a.to(dev), b.to(dev), 1, 3), M[1:3])
+    # identical sets: every cloud is its own nearest neighbour under EMD
+    S = ops.pairwise_emd(a.to(dev), a.to(dev))
+    assert torch.equal(S.argmin(dim=1).cpu(), torch.arange(4))
+    res = metrics.compute_all_metrics(a.to(dev), b.to(dev), batch_size=2)
+    assert set(res) == {"mmd-CD", "cov-CD", "mmd-EMD", "cov-EMD", "1-NN-CD-acc", "1-NN-EMD-acc"}
+
+
+# ------------------------------------------------------------------------------------------------
 # GEMM core
 # ------------------------------------------------------------------------------------------------
 def _gemm_ref(A, W, bias, epi, resid=None, gate=None, rows_per_gate=1):

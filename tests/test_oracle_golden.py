@@ -206,3 +206,26 @@ def test_pairwise_cd_and_metrics_match_reference(oracle_nn):
     # python-level restatement through nn_fn agrees with the C one
     M2 = O.pairwise_cd(ref, smp, lambda a, b: (lambda r: (r[0], r[2]))(c_nn_distance(oracle_nn, a, b)))
     assert torch.allclose(M2, M_rs, rtol=1e-6, atol=0)
+
+
+def test_emd_oracle_known_answers():
+    """The approximate-EMD restatement (oracle/emd_oracle.c) on cases with a known optimum: a single pair of points
+    (cost = their distance), and a well-separated cloud against a shuffled, slightly shifted copy of itself (the
+    auction must find the permutation: cost = sum of the shifts)."""
+    import ctypes as C
+    L = C.CDLL(os.path.join(ROOT, "oracle", "liboracle_emd.so"))
+    L.oracle_match_cost.argtypes = [C.c_int] * 3 + [C.c_void_p] * 4
+    a = torch.tensor([[[0.1, 0.2, 0.3]]])
+    b = torch.tensor([[[0.4, -0.2, 0.3]]])
+    c = torch.empty(1)
+    L.oracle_match_cost(1, 1, 1, a.data_ptr(), b.data_ptr(), c.data_ptr(), None)
+    assert abs(float(c[0]) - 0.5) < 1e-4
+    g = torch.Generator().manual_seed(0)
+    grid = torch.stack(torch.meshgrid(torch.arange(4.), torch.arange(4.), torch.arange(4.), indexing="ij"), -1).reshape(1, 64, 3)
+    shift = torch.rand((1, 64, 3), generator=g) * 0.02
+    perm = torch.randperm(64, generator=g)
+    b = (grid + shift)[:, perm].contiguous()
+    c = torch.empty(1)
+    L.oracle_match_cost(1, 64, 64, grid.contiguous().data_ptr(), b.data_ptr(), c.data_ptr(), None)
+    want = float(shift.norm(dim=-1).sum())
+    assert abs(float(c[0]) - want) < 1e-3 * want + 1e-5, (float(c[0]), want)
