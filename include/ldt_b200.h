@@ -181,6 +181,7 @@ enum ldt_predictor {
   LDT_PRED_REVERSE_DIFFUSION = 1, /* :141-150 */
   LDT_PRED_EULER_MARUYAMA = 2,    /* :182-191 */
   LDT_PRED_DDIM = 3,              /* :164-180 */
+  LDT_PRED_CORRECTOR = 4,         /* the update of LangevinCorrector / AncestralCorrector, :193-229 */
 };
 /* coef layout per step (8 floats): [0]=sqrt(var(t)) [1..7] predictor specific, see ldt_b200/sde.py */
 #define LDT_SDE_COEF_STRIDE 8
@@ -193,12 +194,50 @@ int ldt_sde_step(int predictor, long long numel, const float* x, const float* pa
                  unsigned long long seed, unsigned long long offset, unsigned long long offset_per_step,
                  int rng_grid, float* x_next, float* x_mean, void* stream);
 
+/* PNDM pieces (diffusion_continuous.py:260-316).
+ * ldt_pndm_transfer: out = x + coef[0] * (coef[1] * x - coef[2] * et)  -- transfer() :264-274; coef is a DEVICE array of
+ *   three floats (at_next - at, 1/(sqrt(at)(sqrt(at)+sqrt(at_next))), 1/(sqrt(at)(sqrt((1-at_next)at)+sqrt((1-at)at_next)))).
+ * ldt_lincomb4: out = scale * (((c0*a0 + c1*a1) + c2*a2) + c3*a3) -- the Runge-Kutta (:284) and linear multistep (:300)
+ *   noise combinations.  Both are rounded like the reference's torch expression. */
+int ldt_pndm_transfer(long long numel, const float* x, const float* et, const float* coef, float* out, void* stream);
+int ldt_lincomb4(long long numel, float c0, const float* a0, float c1, const float* a1, float c2, const float* a2,
+                 float c3, const float* a3, float scale, float* out, void* stream);
+
+/* out[0] = mean over rows of ||x[row, 0:row_len]||_2 (norms [rows] is scratch): the grad / noise norms of the Langevin
+ * corrector, diffusion_continuous.py:205-206.  Fixed summation order (deterministic). */
+int ldt_batch_mean_norm(int rows, long long row_len, const float* x, float* norms, float* out, void* stream);
+
 /* *step_index += 1 (device side), so a captured step graph can be replayed N times. */
 int ldt_advance_step(int* step_index, void* stream);
 
 /* out[0:row_len] = table[*step_index, 0:row_len]  (f32, row_len % 4 == 0).  Used to pull the current
  * step's AdaLN modulation rows out of the per-timestep table ("batch-invariant AdaLN"). */
 int ldt_select_row(const float* table, long long row_len, const int* step_index, float* out, void* stream);
+
+/* Per-step conditioning vector of CONDITIONAL sampling (completion / class-conditional):
+ *   c[r,:] = table[*step_index,:] (+ extra[r,:]);  silu_out[r,:] = bf16(SiLU(c[r,:]))
+ * table [N,D] f32 holds TimeEmbedding(t_i) for every step (batch-invariant), extra [R,D] f32 (or NULL) the per-sample
+ * image / label embedding: model/scorenet/score.py:134-135 `c = t_emb + condition[1]`, followed by the SiLU of every
+ * adaLN branch (model/layers.py:172).  c_out [R,D] f32 may be NULL.  step_index NULL = row 0. */
+int ldt_cond_silu(int R, int D, const float* table, const int* step_index, const float* extra, float* c_out,
+                  void* silu_out /* bf16 [R,D] */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Point-set prologue of the completion path
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Furthest point sampling: idx [b,m] i32 = indices of m points of each cloud xyz [b,n,3] f32 (n <= 8192), starting
+ * from index 0, each next point the one farthest from the selected set (ties -> lowest index).  Replaces
+ * pointnet2_utils.furthest_point_sample (un-vendored dependency; call sites model/Compressor/layers.py:106 and
+ * completion_trainer/Latent_SDE_Trainer.py:182-183).  Points with |p|^2 <= min_sq_norm are never selected
+ * (pointnet2_ops uses 1e-3; a negative value disables the rule, matching the reference's in-tree
+ * model/functional/src/sampling/sampling.cu:86-167). */
+int ldt_furthest_point_sample(int b, int n, int m, const float* xyz, float min_sq_norm, int* idx, void* stream);
+
+/* k nearest neighbours: idx [b,s,k] i32 = the k points of xyz [b,n,3] closest to each of centers [b,s,3], in order of
+ * increasing squared distance (ties -> lowest index).  Replaces knn_point = square_distance + torch.topk
+ * (model/Compressor/layers.py:63-98), which builds a dense [b,s,n] matrix and returns the set in unspecified order. */
+int ldt_knn_indices(int b, int n, int s, int k, const float* xyz, const float* centers, int* idx, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Device properties needed by the host mirror

@@ -22,6 +22,7 @@ PRED_ANCESTRAL = 0
 PRED_REVERSE_DIFFUSION = 1
 PRED_EULER_MARUYAMA = 2
 PRED_DDIM = 3
+PRED_CORRECTOR = 4
 SDE_COEF_STRIDE = 8
 
 
@@ -73,8 +74,15 @@ PROTOTYPES = {
     "ldt_sde_step": (C.c_int, [C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_void_p]),
+    "ldt_pndm_transfer": (C.c_int, [C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldt_lincomb4": (C.c_int, [C.c_longlong, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_float,
+                              C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
+    "ldt_batch_mean_norm": (C.c_int, [C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldt_advance_step": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ldt_select_row": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldt_cond_silu": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldt_furthest_point_sample": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
+    "ldt_knn_indices": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,154 @@
+"""Host mirror of the completion prologue: ``ConditionNet`` (reference model/scorenet/score.py:13-44) and the
+``LocalGrouper`` it is built on (reference model/Compressor/layers.py:288-319, 225-256, 130-177).
+
+Runs ONCE per ``sample()`` call, before the reverse-SDE loop (completion_trainer/Latent_SDE_Trainer.py:150-151), so
+it is a prologue, not the hot loop.  What is B200-native here is the point-set part the reference cannot run without
+its un-vendored ``pointnet2_ops`` dependency: furthest point sampling and k-NN grouping are sm_100a kernels behind the
+C ABI (``ldt_furthest_point_sample``, ``ldt_knn_indices``); the small dense layers around them (ResNet18 stem on the
+image, 1x1 convolutions with BatchNorm on 32 groups x 8 neighbours) are plain torch modules with the reference's
+parameter names, so reference checkpoints load with ``strict=True``:
+
+  c_net.pc_conv_in, c_net.group.{affine_alpha, affine_beta, extraction.transfer.net.{0,1},
+  extraction.operation.0.{net1.{0,1}, net2.0}}, c_net.pc_conv_out, c_net.resnet.{0,1,4,5}.*, c_net.ln, c_net.conv_out
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+def gather_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """points [B,N,C], idx [B,...] (any integer dtype) -> [B,...,C]   (index_points, Compressor/layers.py:46-62)."""
+    B = points.shape[0]
+    flat = idx.reshape(B, -1).long()
+    out = torch.gather(points, 1, flat.unsqueeze(-1).expand(-1, -1, points.shape[-1]))
+    return out.reshape(*idx.shape, points.shape[-1])
+
+
+def furthest_point_sample(xyz: torch.Tensor, npoint: int) -> torch.Tensor:
+    """Drop-in for ``pointnet2_utils.furthest_point_sample(xyz [B,N,3], npoint) -> int32 [B,npoint]``."""
+    return ops.furthest_point_sample(xyz.contiguous().float(), npoint)
+
+
+def cluster(xyz: torch.Tensor, groups: int, k: int, center=None):
+    """(new_xyz [B,S,3], center_idx [B,S] | None, group_idx [B,S,k]) -- Compressor/layers.py:101-112."""
+    xyz = xyz.contiguous().float()
+    if center is None:
+        center_idx = furthest_point_sample(xyz, groups).long()
+        new_xyz = gather_points(xyz, center_idx)
+    else:
+        new_xyz, center_idx = center.contiguous().float(), None
+    group_idx = ops.knn_indices(k, xyz, new_xyz.contiguous()).long()
+    return new_xyz, center_idx, group_idx
+
+
+class _ConvBNAct(nn.Module):
+    """Conv1d(k=1) + BatchNorm1d + ReLU under the key ``net`` (ConvBNReLU1D, Compressor/layers.py:115-127)."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.net = nn.Sequential(nn.Conv1d(cin, cout, 1), nn.BatchNorm1d(cout), nn.ReLU(inplace=True))
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class _ConvBNActRes(nn.Module):
+    """Residual 1x1 block, keys ``net1`` / ``net2`` (ConvBNReLURes1D with groups=1, Compressor/layers.py:130-160)."""
+
+    def __init__(self, ch):
+        super().__init__()
+        self.net1 = nn.Sequential(nn.Conv1d(ch, ch, 1), nn.BatchNorm1d(ch), nn.ReLU(inplace=True))
+        self.net2 = nn.Sequential(nn.Conv1d(ch, ch, 1))
+
+    def forward(self, x):
+        return F.relu(self.net2(self.net1(x)) + x)
+
+
+class _PreExtraction(nn.Module):
+    """[B,S,k,d] -> [B,D,S]: per-neighbour 1x1 layers then max over the k neighbours (Compressor/layers.py:163-192)."""
+
+    def __init__(self, channels, out_channels, use_xyz=True):
+        super().__init__()
+        self.transfer = _ConvBNAct((3 if use_xyz else 0) + 2 * channels, out_channels)
+        self.operation = nn.Sequential(_ConvBNActRes(out_channels))
+
+    def forward(self, x):
+        B, S, k, d = x.shape
+        y = self.operation(self.transfer(x.permute(0, 1, 3, 2).reshape(B * S, d, k)))
+        return y.amax(dim=-1).reshape(B, S, -1).permute(0, 2, 1)
+
+
+class LocalGrouper(nn.Module):
+    """FPS centres + k-NN groups + normalised group features -> per-group feature (Compressor/layers.py:288-319)."""
+
+    def __init__(self, in_channels, use_xyz=True, normalize="anchor"):
+        super().__init__()
+        self.use_xyz = use_xyz
+        self.normalize = normalize.lower() if normalize is not None else None
+        if self.normalize not in ("center", "anchor"):
+            self.normalize = None
+        if self.normalize is not None:
+            add = 3 if use_xyz else 0
+            self.affine_alpha = nn.Parameter(torch.ones([1, 1, 1, in_channels + add]))
+            self.affine_beta = nn.Parameter(torch.zeros([1, 1, 1, in_channels + add]))
+        self.extraction = _PreExtraction(in_channels, in_channels)
+
+    def forward(self, xyz, feature, groups, k):
+        """xyz [B,3,N], feature [B,D,N] -> (new_xyz [B,3,S], new_feature [B,D,S])."""
+        pts = xyz.transpose(1, 2)
+        fea = feature.transpose(1, 2)
+        B = pts.shape[0]
+        with torch.no_grad():
+            new_xyz, fps_idx, idx = cluster(pts, groups, k)
+        anchor_fea = gather_points(fea, fps_idx)                       # [B,S,D]
+        grouped = gather_points(fea, idx)                              # [B,S,k,D]
+        if self.use_xyz:
+            grouped = torch.cat([grouped, gather_points(pts, idx)], dim=-1)
+        if self.normalize is not None:
+            if self.normalize == "center":
+                mean = grouped.mean(dim=2, keepdim=True)
+            else:
+                mean = (torch.cat([anchor_fea, new_xyz], dim=-1) if self.use_xyz else anchor_fea).unsqueeze(-2)
+            centred = grouped - mean
+            std = torch.std(centred.reshape(B, -1), dim=-1, keepdim=True)[:, :, None, None]
+            grouped = self.affine_alpha * (centred / (std + 1e-5)) + self.affine_beta
+        x = torch.cat([grouped, anchor_fea.unsqueeze(2).expand(-1, -1, k, -1)], dim=-1)
+        return new_xyz.transpose(1, 2), self.extraction(x)
+
+
+class ConditionNet(nn.Module):
+    """(pts_cond [B,hidden,32], img_cond [B,p_dim]) from {'img': [B,3,H,W], 'pts': [B,N,3]} (score.py:13-44)."""
+
+    def __init__(self, hidden_size, p_dim, patch_size=16, img_condition=True, pt_condition=True):
+        super().__init__()
+        self.hidden_size, self.patch_size = hidden_size, patch_size
+        self.img_condition, self.pt_condition = img_condition, pt_condition
+        if pt_condition:
+            self.pc_conv_in = nn.Conv1d(3, 128, 1)
+            self.group = LocalGrouper(128, True, normalize="center")
+            self.pc_conv_out = nn.Conv1d(128, hidden_size, 1)
+        if img_condition:
+            from torchvision import models
+            trunk = models.resnet18(weights=None)
+            self.resnet = nn.Sequential(*list(trunk.children())[:-4])   # stem + layer1 + layer2 -> 128 channels
+            self.ln = nn.Linear(128, p_dim)
+        self.conv_out = nn.Conv1d(hidden_size, hidden_size, 1)          # present in checkpoints, unused (score.py:29)
+
+    def forward(self, condition):
+        dev = self.conv_out.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("ldt_b200.ConditionNet runs on CUDA only (FPS / k-NN kernels have no CPU fallback)")
+        pts_cond, img_cond = 0.0, 0.0
+        if "img" in condition and self.img_condition:
+            img = condition["img"].to(dev)
+            img_cond = self.ln(F.adaptive_max_pool2d(self.resnet(img), 1).squeeze())
+        if "pts" in condition and self.pt_condition:
+            pts = condition["pts"].to(dev).transpose(1, 2)
+            x = self.pc_conv_in(pts)
+            _, x = self.group(pts, x, self.patch_size, x.shape[1] // self.patch_size * 2)
+            pts_cond = self.pc_conv_out(x)
+        return pts_cond, img_cond

@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(int R, int Kin, int 
 //   reverse diffusion:  [1] f coeff (-0.5 g2) [2] g2 * (0.5 if pf else 1) [3] dt   [4] g (0 if pf)  [5] sqrt(dt)
 //   euler-maruyama:     [1] f coeff          [2] g2 * (0.5 if pf else 1) [3] dt(<0) [4] sqrt(g2)*sqrt(-dt) (0 if pf)
 //   ddim:               [1] sqrt(at_next)    [2] sqrt(1-at)        [3] sqrt(at)     [4] sqrt(1-at_next)
+//   corrector:          [1] step_size        [2] sqrt(2 * step_size)
 // ------------------------------------------------------------------------------------------------
 template <int PRED>
 __device__ __forceinline__ void sde_update(float x, float prm, float z, const float* __restrict__ c, float& xn,
@@ -197,10 +198,14 @@ __device__ __forceinline__ void sde_update(float x, float prm, float z, const fl
     const float f = __fsub_rn(__fmul_rn(c[1], x), __fmul_rn(c[2], score));
     xm = __fadd_rn(x, __fmul_rn(f, c[3]));
     xn = __fadd_rn(xm, __fmul_rn(c[4], z));
-  } else {  // DDIM (sigma = 0)
+  } else if (PRED == LDT_PRED_DDIM) {  // sigma = 0
     const float a = __fdiv_rn(__fmul_rn(c[1], __fsub_rn(x, __fmul_rn(c[2], prm))), c[3]);
     xm = __fadd_rn(a, __fmul_rn(c[4], prm));
     xn = xm;
+  } else {  // corrector step (Langevin / ancestral corrector :193-229): x_mean = x + step*grad, x = x_mean + sqrt(2 step)*z
+    const float score = __fdiv_rn(-prm, c[0]);
+    xm = __fadd_rn(x, __fmul_rn(c[1], score));
+    xn = __fadd_rn(xm, __fmul_rn(c[2], z));
   }
 }
 
@@ -252,6 +257,75 @@ __global__ void __launch_bounds__(256) select_row_kernel(const float* __restrict
   float4* dst = reinterpret_cast<float4*>(out);
   const long long n4 = row_len >> 2;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += gridDim.x * 256LL) dst[i] = src[i];
+}
+
+// c[r, :] = table[step, :] (+ extra[r, :]);  silu_out[r, :] = bf16(SiLU(c[r, :])).
+// The per-step conditioning vector of conditional sampling: table holds TimeEmbedding(t_i) for every step i
+// (batch-invariant), extra the per-sample image / label embedding (score.py:135: c = t_emb + condition[1]).
+// Same operation order as skinny_linear_kernel's `(acc + b) + extra`, so c is bit-identical to the eager forward.
+__global__ void __launch_bounds__(256) cond_silu_kernel(int R, int D, const float* __restrict__ table,
+                                                      const int* __restrict__ step_index, const float* __restrict__ extra,
+                                                      float* __restrict__ c_out, __nv_bfloat16* __restrict__ silu_out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const float* row = table + static_cast<size_t>(step_index ? *step_index : 0) * D;
+  const long long total = static_cast<long long>(R) * D;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int n = static_cast<int>(i % D);
+    float v = row[n];
+    if (extra) v += extra[i];
+    if (c_out) c_out[i] = v;
+    silu_out[i] = __float2bfloat16_rn(silu_f(v));
+  }
+}
+
+// ---- PNDM (diffusion_continuous.py:260-316) ------------------------------------------------------------------
+// transfer(): x_next = x + d * (a * x - b * et) with the three step scalars read from device memory (they are produced
+// by the reference's own torch expression on 1-element tensors, so they are bit-identical); explicit roundings in
+// the reference's operation order.
+__global__ void __launch_bounds__(256) pndm_transfer_kernel(long long numel, const float* __restrict__ x,
+                                                          const float* __restrict__ et, const float* __restrict__ coef,
+                                                          float* __restrict__ out) {
+  const float d = coef[0], a = coef[1], b = coef[2];
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < numel; i += gridDim.x * 256LL)
+    out[i] = __fadd_rn(x[i], __fmul_rn(d, __fsub_rn(__fmul_rn(a, x[i]), __fmul_rn(b, et[i]))));
+}
+
+// out = scale * (((c0*a0 + c1*a1) + c2*a2) + c3*a3): the Runge-Kutta / Adams-Bashforth noise combinations (:284,300).
+__global__ void __launch_bounds__(256) lincomb4_kernel(long long numel, float c0, const float* __restrict__ a0, float c1,
+                                                     const float* __restrict__ a1, float c2, const float* __restrict__ a2,
+                                                     float c3, const float* __restrict__ a3, float scale,
+                                                     float* __restrict__ out) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < numel; i += gridDim.x * 256LL) {
+    float v = __fadd_rn(__fmul_rn(c0, a0[i]), __fmul_rn(c1, a1[i]));
+    v = __fadd_rn(v, __fmul_rn(c2, a2[i]));
+    v = __fadd_rn(v, __fmul_rn(c3, a3[i]));
+    out[i] = __fmul_rn(scale, v);
+  }
+}
+
+// norms[b] = ||x[b, :]||_2 ; then out[0] = mean_b norms[b] (fixed summation order: deterministic).  The two global
+// norms of the Langevin corrector (:205-206).
+__global__ void __launch_bounds__(256) row_norm_kernel(long long L, const float* __restrict__ x, float* __restrict__ norms) {
+  __shared__ float red[8];
+  const float* row = x + static_cast<size_t>(blockIdx.x) * L;
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < L; i += 256) acc = fmaf(row[i], row[i], acc);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    norms[blockIdx.x] = sqrtf(t);
+  }
+}
+__global__ void mean_kernel(int n, const float* __restrict__ v, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < n; ++i) t += v[i];
+    out[0] = t / static_cast<float>(n);
+  }
 }
 
 }  // namespace ldt
@@ -345,6 +419,7 @@ extern "C" int ldt_sde_step(int predictor, long long numel, const float* x, cons
     case LDT_PRED_REVERSE_DIFFUSION: LDT_SDE_LAUNCH(LDT_PRED_REVERSE_DIFFUSION); break;
     case LDT_PRED_EULER_MARUYAMA: LDT_SDE_LAUNCH(LDT_PRED_EULER_MARUYAMA); break;
     case LDT_PRED_DDIM: LDT_SDE_LAUNCH(LDT_PRED_DDIM); break;
+    case LDT_PRED_CORRECTOR: LDT_SDE_LAUNCH(LDT_PRED_CORRECTOR); break;
     default: set_last_error("ldt_sde_step: unknown predictor %d", predictor); return LDT_ERR_INVALID;
   }
 #undef LDT_SDE_LAUNCH
@@ -364,5 +439,43 @@ extern "C" int ldt_select_row(const float* table, long long row_len, const int* 
   const int grid = static_cast<int>(std::min<long long>((row_len / 4 + 255) / 256, static_cast<long long>(num_sms()) * 4));
   LDT_CUDA_OK(launch_pdl(select_row_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), table, row_len,
                          step_index, out));
+  return LDT_OK;
+}
+
+extern "C" int ldt_cond_silu(int R, int D, const float* table, const int* step_index, const float* extra, float* c_out,
+                             void* silu_out, void* stream) {
+  LDT_REQUIRE(R > 0 && D > 0 && table && silu_out, LDT_ERR_INVALID, "ldt_cond_silu: bad arguments R=%d D=%d", R, D);
+  const long long total = static_cast<long long>(R) * D;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(num_sms()) * 8));
+  LDT_CUDA_OK(launch_pdl(cond_silu_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), R, D, table,
+                         step_index, extra, c_out, static_cast<__nv_bfloat16*>(silu_out)));
+  return LDT_OK;
+}
+
+extern "C" int ldt_pndm_transfer(long long numel, const float* x, const float* et, const float* coef, float* out, void* stream) {
+  LDT_REQUIRE(numel >= 0 && (numel == 0 || (x && et && coef && out)), LDT_ERR_INVALID, "ldt_pndm_transfer: bad arguments");
+  if (numel == 0) return LDT_OK;
+  const int grid = static_cast<int>(std::min<long long>((numel + 255) / 256, static_cast<long long>(num_sms()) * 8));
+  pndm_transfer_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(numel, x, et, coef, out);
+  LDT_CUDA_OK(cudaGetLastError());
+  return LDT_OK;
+}
+
+extern "C" int ldt_lincomb4(long long numel, float c0, const float* a0, float c1, const float* a1, float c2, const float* a2,
+                            float c3, const float* a3, float scale, float* out, void* stream) {
+  LDT_REQUIRE(numel >= 0 && (numel == 0 || (a0 && a1 && a2 && a3 && out)), LDT_ERR_INVALID, "ldt_lincomb4: bad arguments");
+  if (numel == 0) return LDT_OK;
+  const int grid = static_cast<int>(std::min<long long>((numel + 255) / 256, static_cast<long long>(num_sms()) * 8));
+  lincomb4_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(numel, c0, a0, c1, a1, c2, a2, c3, a3, scale, out);
+  LDT_CUDA_OK(cudaGetLastError());
+  return LDT_OK;
+}
+
+extern "C" int ldt_batch_mean_norm(int rows, long long row_len, const float* x, float* norms, float* out, void* stream) {
+  LDT_REQUIRE(rows > 0 && row_len > 0 && x && norms && out, LDT_ERR_INVALID, "ldt_batch_mean_norm: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  row_norm_kernel<<<rows, 256, 0, s>>>(row_len, x, norms);
+  mean_kernel<<<1, 32, 0, s>>>(rows, norms, out);
+  LDT_CUDA_OK(cudaGetLastError());
   return LDT_OK;
 }

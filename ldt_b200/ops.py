@@ -236,6 +236,30 @@ def sde_step(predictor: int, x, params, z, coef_table, step_index, seed: int, of
               "ldt_sde_step")
 
 
+def pndm_transfer(x, et, coef, out) -> None:
+    with torch.cuda.device(x.device), _launch("pndm_transfer"):
+        check(load().ldt_pndm_transfer(x.numel(), ptr(x), ptr(et), ptr(coef), ptr(out), stream_ptr()), "ldt_pndm_transfer")
+
+
+def lincomb4(coefs, tensors, scale: float, out) -> None:
+    (c0, c1, c2, c3), (a0, a1, a2, a3) = coefs, tensors
+    with torch.cuda.device(out.device), _launch("lincomb4"):
+        check(load().ldt_lincomb4(out.numel(), c0, ptr(a0), c1, ptr(a1), c2, ptr(a2), c3, ptr(a3), scale, ptr(out),
+                                  stream_ptr()), "ldt_lincomb4")
+
+
+def batch_mean_norm(x: torch.Tensor) -> torch.Tensor:
+    """0-dim tensor: mean over the batch of the per-sample L2 norms (torch.norm(x.reshape(B,-1), dim=-1).mean())."""
+    _req(x, torch.float32, "x")
+    B = x.shape[0]
+    norms = torch.empty((B,), dtype=torch.float32, device=x.device)
+    out = torch.empty((1,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device), _launch("batch_mean_norm", 2):
+        check(load().ldt_batch_mean_norm(B, x.numel() // B, ptr(x), ptr(norms), ptr(out), stream_ptr()),
+              "ldt_batch_mean_norm")
+    return out[0]
+
+
 def advance_step(step_index) -> None:
     with torch.cuda.device(step_index.device), _launch("advance_step"):
         check(load().ldt_advance_step(ptr(step_index), stream_ptr()), "ldt_advance_step")
@@ -245,6 +269,39 @@ def select_row(table, step_index, out) -> None:
     with torch.cuda.device(out.device), _launch("select_row"):
         check(load().ldt_select_row(ptr(table), table.shape[1], ptr(step_index), ptr(out), stream_ptr()),
               "ldt_select_row")
+
+
+def cond_silu(table, step_index, extra, c_out, silu_out) -> None:
+    R, D = silu_out.shape
+    with torch.cuda.device(silu_out.device), _launch("cond_silu"):
+        check(load().ldt_cond_silu(R, D, ptr(table), ptr(step_index), ptr(extra), ptr(c_out), ptr(silu_out), stream_ptr()),
+              "ldt_cond_silu")
+
+
+def furthest_point_sample(xyz: torch.Tensor, m: int, min_sq_norm: float = 1e-3) -> torch.Tensor:
+    """idx [b,m] int32 -- pointnet2_utils.furthest_point_sample(xyz [b,n,3], m) (see include/ldt_b200.h)."""
+    _req(xyz, torch.float32, "xyz")
+    if xyz.dim() != 3 or xyz.shape[2] != 3:
+        raise RuntimeError(f"expected [b,n,3], got {tuple(xyz.shape)}")
+    b, n = xyz.shape[0], xyz.shape[1]
+    idx = torch.empty((b, m), dtype=torch.int32, device=xyz.device)
+    with torch.cuda.device(xyz.device), _launch("fps"):
+        check(load().ldt_furthest_point_sample(b, n, m, ptr(xyz), min_sq_norm, ptr(idx), stream_ptr()),
+              "ldt_furthest_point_sample")
+    return idx
+
+
+def knn_indices(k: int, xyz: torch.Tensor, centers: torch.Tensor) -> torch.Tensor:
+    """idx [b,s,k] int32 -- knn_point(k, xyz [b,n,3], centers [b,s,3]) (model/Compressor/layers.py:86-98)."""
+    _req(xyz, torch.float32, "xyz")
+    _req(centers, torch.float32, "centers")
+    if xyz.dim() != 3 or centers.dim() != 3 or xyz.shape[2] != 3 or centers.shape[2] != 3 or xyz.shape[0] != centers.shape[0]:
+        raise RuntimeError(f"expected [b,n,3] and [b,s,3], got {tuple(xyz.shape)} and {tuple(centers.shape)}")
+    b, n, s = xyz.shape[0], xyz.shape[1], centers.shape[1]
+    idx = torch.empty((b, s, k), dtype=torch.int32, device=xyz.device)
+    with torch.cuda.device(xyz.device), _launch("knn"):
+        check(load().ldt_knn_indices(b, n, s, k, ptr(xyz), ptr(centers), ptr(idx), stream_ptr()), "ldt_knn_indices")
+    return idx
 
 
 __all__ = [n for n in dir() if not n.startswith("_")] + ["_lib"]

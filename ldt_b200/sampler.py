@@ -47,24 +47,52 @@ def modulation_table(score, P, timesteps: torch.Tensor, chunk: int = 256) -> tor
     for s in range(0, N, chunk):
         e = min(N, s + chunk)
         R = e - s
-        c = torch.empty((R, score.hidden_size), dtype=torch.float32, device=dev)
-        sc = torch.empty((R, score.hidden_size), dtype=torch.bfloat16, device=dev)
-        scratch = torch.empty((R, score.hidden_size + 2 * half), dtype=torch.float32, device=dev)
+        c = torch.empty((R, score.t_dim), dtype=torch.float32, device=dev)
+        sc = torch.empty((R, score.t_dim), dtype=torch.bfloat16, device=dev)
+        scratch = torch.empty((R, score.t_dim + 2 * half), dtype=torch.float32, device=dev)
         ops.time_embedding(timesteps[s:e].contiguous(), P["freq"], w0, b0, w1, b1, None, c, sc, scratch)
         ops.gemm(sc, P["w_ada"], P["b_ada"], table[s:e], ops.EPI_BIAS_F32)
+    return table
+
+
+def time_embedding_table(score, P, timesteps: torch.Tensor) -> torch.Tensor:
+    """TimeEmbedding(t_i) for every timestep: f32 [N, t_dim] (model/layers.py:38-41)."""
+    N, dev = timesteps.shape[0], timesteps.device
+    half = (score.t_dim // 4) // 2
+    w0, b0, w1, b1 = P["te"]
+    table = torch.empty((N, score.t_dim), dtype=torch.float32, device=dev)
+    sc = torch.empty((N, score.t_dim), dtype=torch.bfloat16, device=dev)
+    scratch = torch.empty((N, score.t_dim + 2 * half), dtype=torch.float32, device=dev)
+    ops.time_embedding(timesteps.contiguous(), P["freq"], w0, b0, w1, b1, None, table, sc, scratch)
     return table
 
 
 class StepGraph:
     """One captured sampler step, replayable; owns the loop state buffers."""
 
-    def __init__(self, score, sde, B, N, predictor, time_eps, probability_flow, device, use_graph=True):
+    def __init__(self, score, sde, B, N, predictor, time_eps, probability_flow, device, use_graph=True,
+                 per_sample_c=False, cross_attention=False):
         self.score, self.B, self.N = score, B, N
         P = score.packed()
         self.P = P
         self.coef, self.timesteps = sde.step_coefficients(predictor, N, time_eps, probability_flow, device)
-        self.table = modulation_table(score, P, self.timesteps)
-        self.ws = score._workspace(B, 1, device)
+        # Conditional sampling (score.py:134-135,148-149).  per_sample_c: c = t_emb(t_i) + extra[b] differs per sample,
+        # so the adaLN GEMM runs every step on [B, t_dim] (1.6 % of the step's MACs at B = 64) from a [N, t_dim] table
+        # of time embeddings.  cross_attention: even blocks attend to the condition tokens, whose K/V are projected
+        # once per run (the reference re-projects them every step).  Both live in buffers owned by this plan, so the
+        # captured graph stays valid across runs with new conditions.
+        self.per_sample_c, self.cross_attention = per_sample_c, cross_attention
+        self.extra = torch.zeros((B, score.t_dim), dtype=torch.float32, device=device) if per_sample_c else None
+        self.kv_cond = None
+        if cross_attention:
+            self.kv_cond = [torch.empty((B * score.z_scale, 2 * score.hidden_size), dtype=torch.bfloat16, device=device)
+                            for _ in range((score.num_blocks + 1) // 2)]
+        if per_sample_c:
+            self.table = time_embedding_table(score, P, self.timesteps)
+            self.ws = score._workspace(B, B, device)
+        else:
+            self.table = modulation_table(score, P, self.timesteps)
+            self.ws = score._workspace(B, 1, device)
         self.code = _PRED_CODES[predictor]
         T, D = score.z_scale, score.z_dim
         self.x = torch.empty((B, T, D), dtype=torch.float32, device=device)
@@ -78,10 +106,26 @@ class StepGraph:
         self.graph = None
         self.use_graph = use_graph
 
+    def set_condition(self, cond_tokens, extra) -> None:
+        """Load this run's condition into the plan's buffers (pointers captured by the graph stay the same)."""
+        if self.per_sample_c:
+            self.extra.copy_(extra.float().expand(self.B, self.score.t_dim))
+        if self.cross_attention:
+            for dst, kv in zip(self.kv_cond, self.score.project_condition_tokens(self.P, cond_tokens)):
+                dst.copy_(kv)
+
     def _step_body(self):
         B, T, D = self.x.shape
-        ops.select_row(self.table, self.step, self.mod_cur)
-        self.score.run_tokens(self.P, self.ws, self.x.view(B * T, D), self.mod_cur, 0, self.params.view(B * T, D))
+        if self.per_sample_c:
+            ws = self.ws
+            ops.cond_silu(self.table, self.step, self.extra, None, ws.sc)
+            ops.gemm(ws.sc, self.P["w_ada"], self.P["b_ada"], ws.mod, ops.EPI_BIAS_F32)
+            mod, mod_stride = ws.mod, ws.mod_len
+        else:
+            ops.select_row(self.table, self.step, self.mod_cur)
+            mod, mod_stride = self.mod_cur, 0
+        self.score.run_tokens(self.P, self.ws, self.x.view(B * T, D), mod, mod_stride, self.params.view(B * T, D),
+                              self.kv_cond)
         ops.sde_step(self.code, self.x, self.params, None, self.coef, self.step, self.seed, self.offset,
                      self.offset_per_step, self.rng_grid, self.x, self.x_mean)
         ops.advance_step(self.step)
@@ -118,17 +162,25 @@ class StepGraph:
 _graph_cache: dict = {}
 
 
-def fused_sample_loop(score, sde, x0, N, predictor, time_eps, probability_flow, denoise, use_graph=True):
-    """x0 [B, z_scale, z_dim] on the device -> latent after N reverse steps (x_mean if denoise else x)."""
+def fused_sample_loop(score, sde, x0, N, predictor, time_eps, probability_flow, denoise, use_graph=True,
+                      cond_tokens=None, extra=None):
+    """x0 [B, z_scale, z_dim] on the device -> latent after N reverse steps (x_mean if denoise else x).
+
+    cond_tokens [B, hidden, z_scale] (condition[0], cross-attended by the even blocks) and extra [B, t_dim]
+    (condition[1] or the label embedding, added to the time embedding) select conditional sampling."""
     device = x0.device
     B = x0.shape[0]
+    per_sample_c, cross = extra is not None, cond_tokens is not None
     key = (id(score), id(sde), B, N, predictor, float(time_eps), bool(probability_flow), device, use_graph,
-           score._fingerprint())
+           per_sample_c, cross, score._fingerprint())
     sg = _graph_cache.get(key)
     if sg is None:
         _graph_cache.clear()  # one live plan: the buffers are large (modulation table ~0.6 GB at N=1000)
-        sg = StepGraph(score, sde, B, N, predictor, time_eps, probability_flow, device, use_graph)
+        sg = StepGraph(score, sde, B, N, predictor, time_eps, probability_flow, device, use_graph,
+                       per_sample_c=per_sample_c, cross_attention=cross)
         _graph_cache[key] = sg
+    if per_sample_c or cross:
+        sg.set_condition(cond_tokens, extra)
     gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
     seed, offset = gen.initial_seed(), gen.get_offset()
     sg.run(x0, seed, offset)

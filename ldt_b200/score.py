@@ -77,7 +77,7 @@ def _pad_to(n: int, g: int) -> int:
 class _Workspace:
     """Caller-owned device buffers for one batch size (the kernels never allocate)."""
 
-    def __init__(self, B, tokens, z_dim, hidden, n_blocks, mod_rows, half, device):
+    def __init__(self, B, tokens, z_dim, hidden, n_blocks, mod_rows, half, device, t_dim=None):
         M = B * tokens
         bf, f32 = torch.bfloat16, torch.float32
         self.B, self.M = B, M
@@ -88,10 +88,12 @@ class _Workspace:
         self.qkv = torch.empty((M, 3 * hidden), dtype=bf, device=device)
         self.att = torch.empty((M, hidden), dtype=bf, device=device)
         self.hid = torch.empty((M, 4 * hidden), dtype=bf, device=device)
+        self.t_dim = hidden if t_dim is None else t_dim
         self.set_mod_rows(mod_rows, hidden, half, device)
 
     def set_mod_rows(self, R, hidden, half, device):
         self.R = R
+        hidden = self.t_dim   # c, SiLU(c) and the scratch rows are t_dim wide (== hidden in the shipped configs)
         self.c = torch.empty((R, hidden), dtype=torch.float32, device=device)
         self.sc = torch.zeros((R, hidden), dtype=torch.bfloat16, device=device)
         self.mod = torch.empty((R, self.mod_len), dtype=torch.float32, device=device)
@@ -124,13 +126,13 @@ class Score(nn.Module):
             raise NotImplementedError("ldt_b200.Score: only norm: layer_norm (the shipped configs) is supported")
         if self.dropout != 0:
             raise NotImplementedError("ldt_b200.Score is a sampling path: dropout must be 0")
-        if self.condition:
-            raise NotImplementedError(
-                "ldt_b200.Score: the ConditionNet prologue (score.py:13-44) is not built yet; pass precomputed "
-                "condition tokens as condition=(pts_cond, img_cond) to a model built with condition: False")
         if self.hidden_size % 128 != 0 or self.hidden_size // self.num_heads not in (32, 64) or self.z_scale != 32:
             raise NotImplementedError("ldt_b200.Score: needs hidden_size % 128 == 0, head dim 32 or 64, z_scale 32")
-        # construction order follows score.py:84-97 (blocks, label embedding, ln_in, time embedding, final layer)
+        # construction order follows score.py:65-97 (condition net, blocks, label embedding, ln_in, time embedding,
+        # final layer)
+        if self.condition:
+            from .condition import ConditionNet
+            self.c_net = ConditionNet(self.hidden_size, self.t_dim, patch_size=self.z_scale)
         self.Transformer = nn.ModuleList(
             [_AdaLNBlockParams(self.hidden_size, self.hidden_size, self.t_dim) for _ in range(self.num_blocks)])
         if cfg.num_categorys > 1:
@@ -151,8 +153,13 @@ class Score(nn.Module):
     # weight packing (fp32 parameters -> bf16 K-major GEMM operands), invalidated when any parameter's
     # storage or version changes (EMA.swap_parameters_with_ema replaces p.data, tools/utils.py:80-101)
     # ------------------------------------------------------------------------------------------
+    def _hot_parameters(self):
+        for name, p in self.named_parameters():
+            if not name.startswith("c_net."):   # the prologue runs in torch straight from its parameters
+                yield p
+
     def _fingerprint(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return tuple((p.data_ptr(), p._version) for p in self._hot_parameters())
 
     def packed(self):
         key = self._fingerprint()
@@ -207,7 +214,7 @@ class Score(nn.Module):
         half = (self.t_dim // 4) // 2
         ws = self._ws.get(B)
         if ws is None or ws.h.device != device:
-            ws = _Workspace(B, self.z_scale, self.z_dim, self.hidden_size, self.num_blocks, mod_rows, half, device)
+            ws = _Workspace(B, self.z_scale, self.z_dim, self.hidden_size, self.num_blocks, mod_rows, half, device, self.t_dim)
             self._ws[B] = ws
         elif ws.R != mod_rows:
             ws.set_mod_rows(mod_rows, self.hidden_size, half, device)
@@ -297,11 +304,14 @@ class Score(nn.Module):
             extra = self.LabelEmbedding(label).float().contiguous()
         if condition is not None:
             if isinstance(condition, dict):
-                raise NotImplementedError("ConditionNet prologue not built; pass (pts_cond, img_cond)")
+                if not self.condition:
+                    raise AttributeError("'Score' object has no attribute 'c_net'")   # as the reference (score.py:129)
+                with torch.no_grad():
+                    condition = self.c_net(condition)
             cond_tokens, cond_vec = condition
             if label is None and torch.is_tensor(cond_vec):
-                extra = cond_vec.float().contiguous()  # c = t_emb + condition[1]  (score.py:135)
-            if cond_tokens is not None:
+                extra = cond_vec.float().expand(B, self.t_dim).contiguous()  # c = t_emb + condition[1]  (score.py:135)
+            if torch.is_tensor(cond_tokens):
                 kv_cond = self.project_condition_tokens(P, cond_tokens)
         ws = self._workspace(B, B, x.device)
         with torch.no_grad():

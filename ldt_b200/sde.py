@@ -162,8 +162,19 @@ class DiffusionVPSDE:
 
             from .sampler import fused_sample_loop, find_score_module  # late import (sampler imports Score)
             score_mod = find_score_module(score_fn, self)
-            if score_mod is not None and label is None and condition is None and print_steps is None:
-                return fused_sample_loop(score_mod, self, x, N, predictor, time_eps, probability_flow, denoise)
+            if score_mod is not None and print_steps is None and not isinstance(condition, dict):
+                # the whole loop as one replayed graph; condition = (tokens | None, vector | 0.) as ConditionNet
+                # returns it (completion_trainer/Latent_SDE_Trainer.py:150-151), label -> embedding (score.py:125-126)
+                cond_tokens, extra = None, None
+                if label is not None:
+                    extra = score_mod.LabelEmbedding(label.to(device))
+                if condition is not None:
+                    if torch.is_tensor(condition[0]):
+                        cond_tokens = condition[0].to(device)
+                    if label is None and torch.is_tensor(condition[1]):
+                        extra = condition[1].to(device)
+                return fused_sample_loop(score_mod, self, x, N, predictor, time_eps, probability_flow, denoise,
+                                         cond_tokens=cond_tokens, extra=extra)
 
             # generic path: arbitrary score_fn called once per step, fused update kernel in between
             coef, timesteps = self.step_coefficients(predictor, N, time_eps, probability_flow, device, raw_score=True)

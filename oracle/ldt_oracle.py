@@ -355,3 +355,82 @@ def synth_state_dict(shapes: dict, seed: int) -> dict:
 
 def cfg_ns(**kw):
     return SimpleNamespace(**kw)
+
+
+# --------------------------------------------------------------------------------------------------
+# completion prologue: ConditionNet (model/scorenet/score.py:13-44) over LocalGrouper
+# (model/Compressor/layers.py:288-319).  `fps_fn(xyz [B,N,3], m) -> long [B,m]` stands in for the un-vendored
+# pointnet2_ops call (tests pass oracle/pointops_oracle.c::oracle_fps through ctypes).
+# --------------------------------------------------------------------------------------------------
+def index_points(points, idx):
+    """points [B,N,C], idx [B,...] -> [B,...,C]  (Compressor/layers.py:46-62)."""
+    B = points.shape[0]
+    batch = torch.arange(B).view(B, *([1] * (idx.dim() - 1))).expand_as(idx)
+    return points[batch, idx, :]
+
+
+def knn_point(k, xyz, new_xyz):
+    """Indices [B,S,k] of the k nearest points, by the reference's expanded distance (layers.py:65-98)."""
+    d = -2 * torch.matmul(new_xyz, xyz.permute(0, 2, 1))
+    d = d + torch.sum(new_xyz ** 2, -1)[:, :, None] + torch.sum(xyz ** 2, -1)[:, None, :]
+    return torch.topk(d, k, dim=-1, largest=False, sorted=False)[1]
+
+
+def _bn_eval(sd, prefix, x):
+    return F.batch_norm(x, sd[prefix + "running_mean"], sd[prefix + "running_var"], sd[prefix + "weight"],
+                        sd[prefix + "bias"], training=False, eps=1e-5)
+
+
+def local_grouper(sd, prefix, xyz, feature, groups, k, normalize, fps_fn, use_xyz=True):
+    """xyz [B,3,N], feature [B,D,N] -> (new_xyz [B,3,S], [B,D,S]); eval-mode BatchNorm (layers.py:288-319,163-192)."""
+    pts, fea = xyz.transpose(1, 2), feature.transpose(1, 2)
+    B = pts.shape[0]
+    fps_idx = fps_fn(pts.contiguous(), groups)
+    new_xyz = index_points(pts, fps_idx)
+    idx = knn_point(k, pts, new_xyz)
+    new_feature = index_points(fea, fps_idx)
+    grouped = index_points(fea, idx)
+    if use_xyz:
+        grouped = torch.cat([grouped, index_points(pts, idx)], dim=-1)
+    if normalize == "center":
+        mean = grouped.mean(dim=2, keepdim=True)
+    else:  # anchor
+        mean = (torch.cat([new_feature, new_xyz], dim=-1) if use_xyz else new_feature).unsqueeze(-2)
+    std = torch.std((grouped - mean).reshape(B, -1), dim=-1, keepdim=True)[:, :, None, None]
+    grouped = sd[prefix + "affine_alpha"] * ((grouped - mean) / (std + 1e-5)) + sd[prefix + "affine_beta"]
+    x = torch.cat([grouped, new_feature[:, :, None, :].expand(-1, -1, k, -1)], dim=-1)
+    b, s, kk, d = x.shape
+    x = x.permute(0, 1, 3, 2).reshape(-1, d, kk)
+    e = prefix + "extraction."
+    x = F.relu(_bn_eval(sd, e + "transfer.net.1.", F.conv1d(x, sd[e + "transfer.net.0.weight"], sd[e + "transfer.net.0.bias"])))
+    o = e + "operation.0."
+    y = F.relu(_bn_eval(sd, o + "net1.1.", F.conv1d(x, sd[o + "net1.0.weight"], sd[o + "net1.0.bias"])))
+    x = F.relu(F.conv1d(y, sd[o + "net2.0.weight"], sd[o + "net2.0.bias"]) + x)
+    x = x.max(dim=-1)[0].reshape(b, s, -1).permute(0, 2, 1)
+    return new_xyz.transpose(1, 2), x
+
+
+def _basic_block(sd, p, x, stride):
+    """torchvision BasicBlock in eval mode (the ResNet18 trunk of score.py:24-25)."""
+    y = F.relu(_bn_eval(sd, p + "bn1.", F.conv2d(x, sd[p + "conv1.weight"], None, stride=stride, padding=1)))
+    y = _bn_eval(sd, p + "bn2.", F.conv2d(y, sd[p + "conv2.weight"], None, stride=1, padding=1))
+    if (p + "downsample.0.weight") in sd:
+        x = _bn_eval(sd, p + "downsample.1.", F.conv2d(x, sd[p + "downsample.0.weight"], None, stride=stride))
+    return F.relu(y + x)
+
+
+def condition_net(sd, prefix, img, pts, patch_size, fps_fn):
+    """(pts_cond [B,hidden,patch_size], img_cond [B,p_dim])  (model/scorenet/score.py:31-44)."""
+    r = prefix + "resnet."
+    x = F.relu(_bn_eval(sd, r + "1.", F.conv2d(img, sd[r + "0.weight"], None, stride=2, padding=3)))
+    x = F.max_pool2d(x, 3, stride=2, padding=1)
+    x = _basic_block(sd, r + "4.0.", x, 1)
+    x = _basic_block(sd, r + "4.1.", x, 1)
+    x = _basic_block(sd, r + "5.0.", x, 2)
+    x = _basic_block(sd, r + "5.1.", x, 1)
+    img_cond = F.linear(F.adaptive_max_pool2d(x, 1).squeeze(), sd[prefix + "ln.weight"], sd[prefix + "ln.bias"])
+    p = pts.transpose(1, 2)
+    f = F.conv1d(p, sd[prefix + "pc_conv_in.weight"], sd[prefix + "pc_conv_in.bias"])
+    _, f = local_grouper(sd, prefix + "group.", p, f, patch_size, f.shape[1] // patch_size * 2, "center", fps_fn)
+    pts_cond = F.conv1d(f, sd[prefix + "pc_conv_out.weight"], sd[prefix + "pc_conv_out.bias"])
+    return pts_cond, img_cond

@@ -96,6 +96,32 @@ def gen_score():
         del model
 
 
+def gen_condition():
+    """ConditionNet + conditional Score from the reference, with the un-vendored pointnet2_ops FPS replaced by the C
+    oracle (oracle/pointops_oracle.c); the same stand-in is used by the oracle-vs-golden test."""
+    from tests.helpers import oracle_fps, small_cond_score_cfg
+    sys.modules["pointnet2_ops.pointnet2_utils"].furthest_point_sample = lambda xyz, m: oracle_fps(xyz, m)
+    from model.scorenet.score import Score
+    cfg = small_cond_score_cfg()
+    torch.manual_seed(0)
+    with CudaToCpu():
+        model = Score(cfg).eval()
+        load_synth(model, 17)
+        g = torch.Generator().manual_seed(117)
+        B = 3
+        img = torch.rand((B, 3, 64, 64), generator=g)
+        pts = torch.randn((B, 600, 3), generator=g)
+        pts = pts / pts.norm(dim=-1).max(dim=1)[0][:, None, None]
+        x = torch.randn((B, cfg.z_scale, cfg.z_dim), generator=g)
+        t = torch.rand((B,), generator=g) * 0.98 + 0.01
+        with torch.no_grad():
+            pts_cond, img_cond = model.c_net({"img": img, "pts": pts})
+            params = model(x, t, condition={"img": img, "pts": pts})
+            params_pts_only = model(x, t, condition={"pts": pts})
+    save("condition.npz", img=img, pts=pts, x=x, t=t, pts_cond=pts_cond, img_cond=img_cond, params=params,
+         params_pts_only=params_pts_only)
+
+
 def gen_decoder():
     from model.Compressor.Network import Compressor
     cfg = dict2namespace(airplane_config()).compressor
@@ -161,7 +187,9 @@ def gen_layout():
     from model.scorenet.score import Score
     cfg = dict2namespace(airplane_config())
     cfg.score.num_blocks = 2  # layout per block is identical; keeps the instantiation light
-    lay = {"score_2blocks": [[k, list(v.shape)] for k, v in Score(cfg.score).state_dict().items()],
+    from tests.helpers import small_cond_score_cfg
+    lay = {"score_cond_small": [[k, list(v.shape)] for k, v in Score(small_cond_score_cfg()).state_dict().items()],
+           "score_2blocks": [[k, list(v.shape)] for k, v in Score(cfg.score).state_dict().items()],
            "compressor": [[k, list(v.shape)] for k, v in Compressor(cfg.compressor).state_dict().items()]}
     with open(os.path.join(HERE, "state_dict_layout.json"), "w") as f:
         json.dump(lay, f)
@@ -194,6 +222,6 @@ def gen_nn():
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 1)
-    which = sys.argv[1:] or ["score", "decoder", "sde", "nn", "layout"]
+    which = sys.argv[1:] or ["score", "condition", "decoder", "sde", "nn", "layout"]
     for w in which:
-        {"score": gen_score, "decoder": gen_decoder, "sde": gen_sde, "nn": gen_nn, "layout": gen_layout}[w]()
+        {"score": gen_score, "condition": gen_condition, "decoder": gen_decoder, "sde": gen_sde, "nn": gen_nn, "layout": gen_layout}[w]()

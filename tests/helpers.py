@@ -67,3 +67,37 @@ def assert_bf16_close(got: torch.Tensor, ref: torch.Tensor, extra_rel: float = 0
     bound = ref.abs() * 2.0 ** -8 + (extra_rel + 1e-6) * rms
     bad = (got - ref).abs() > bound
     assert not bad.any(), f"{what}: {int(bad.sum())} elements outside the bf16 bound, worst {(got - ref).abs().max():.3e}"
+
+
+_ORACLE_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+
+
+def _pointops_oracle():
+    import ctypes as C
+    lib = C.CDLL(os.path.join(_ORACLE_DIR, "liboracle_pointops.so"))
+    lib.oracle_fps.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p]
+    lib.oracle_knn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    return lib
+
+
+def oracle_fps(xyz: torch.Tensor, m: int, min_sq_norm: float = 1e-3) -> torch.Tensor:
+    """C-oracle furthest point sampling: xyz [B,N,3] (CPU f32) -> long [B,m]."""
+    x = xyz.detach().cpu().float().contiguous()
+    idx = torch.empty((x.shape[0], m), dtype=torch.int32)
+    _pointops_oracle().oracle_fps(x.shape[0], x.shape[1], m, x.data_ptr(), min_sq_norm, idx.data_ptr())
+    return idx.long()
+
+
+def oracle_knn(k: int, xyz: torch.Tensor, centers: torch.Tensor) -> torch.Tensor:
+    x, c = xyz.detach().cpu().float().contiguous(), centers.detach().cpu().float().contiguous()
+    idx = torch.empty((x.shape[0], c.shape[1], k), dtype=torch.int32)
+    _pointops_oracle().oracle_knn(x.shape[0], x.shape[1], c.shape[1], k, x.data_ptr(), c.data_ptr(), idx.data_ptr())
+    return idx.long()
+
+
+def small_cond_score_cfg() -> SimpleNamespace:
+    """Reduced completion score config: the shipped score config with ``condition: True`` (no completion yaml ships
+    in the reference's experiments/), narrowed like small_score_cfg()."""
+    c = small_score_cfg()
+    c.condition = True
+    return c

@@ -10,8 +10,9 @@ import os
 import pytest
 import torch
 
+from ldt_b200 import ops
 from oracle import ldt_oracle as O
-from tests.helpers import airplane_config, assert_bf16_close, golden, ns, rel_rms_err, rms_rel_err
+from tests.helpers import airplane_config, assert_bf16_close, golden, ns, rel_rms_err, rms_rel_err, small_score_cfg
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -456,3 +457,70 @@ def test_sde_step_philox_noise_equals_torch_randn_like(dev, numel_shape):
     coef2 = coef.repeat(2, 1)
     ops.sde_step(0, x, prm, None, coef2, step, seed, off, per_call, grid, xn, None)
     assert torch.equal(xn, want2)
+
+
+# ------------------------------------------------------------------------------------------------
+# point-set prologue: furthest point sampling, k-NN grouping, per-step conditioning vector
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("b,n,m,rule", [(3, 600, 32, 1e-3), (2, 2048, 2048, 1e-3), (2, 3500, 2048, 1e-3), (1, 8192, 512, -1.0),
+                                         (4, 100, 100, -1.0), (2, 1, 1, -1.0), (2, 513, 7, 1e-3)])
+def test_fps_bit_exact_vs_oracle(dev, b, n, m, rule):
+    from tests.helpers import oracle_fps
+    g = torch.Generator().manual_seed(n + m)
+    x = torch.randn((b, n, 3), generator=g)
+    x = x / x.norm(dim=-1).max(dim=1)[0][:, None, None]      # unit-sphere normalised like ShapeNet_55.py:50-54
+    if n >= 100:
+        x[:, 10:14] = x[:, 50:54]                              # duplicate points: exact ties
+    got = ops.furthest_point_sample(x.to(dev), m, rule)
+    assert got.dtype == torch.int32 and got.shape == (b, m)
+    assert torch.equal(got.cpu().long(), oracle_fps(x, m, rule))
+
+
+def test_fps_rejects_bad_inputs(dev):
+    x = torch.randn((2, 64, 3), device=dev)
+    with pytest.raises(RuntimeError):
+        ops.furthest_point_sample(x, 65)
+    with pytest.raises(RuntimeError):
+        ops.furthest_point_sample(x.cpu(), 8)
+    with pytest.raises(RuntimeError):
+        ops.furthest_point_sample(torch.randn((1, 9000, 3), device=dev), 8)
+
+
+@pytest.mark.parametrize("b,n,s,k", [(3, 600, 32, 8), (2, 2048, 32, 128), (2, 2048, 2048, 16), (1, 50, 50, 50)])
+def test_knn_vs_oracle_and_reference_formula(dev, b, n, s, k):
+    from tests.helpers import oracle_knn
+    g = torch.Generator().manual_seed(n + s + k)
+    x = torch.rand((b, n, 3), generator=g)
+    c = x[:, torch.randperm(n, generator=g)[:s]].contiguous()
+    got = ops.knn_indices(k, x.to(dev), c.to(dev)).cpu().long()
+    assert torch.equal(got, oracle_knn(k, x, c))               # order (distance, index) and ties, bit for bit
+    # the reference's knn_point (expanded |a|^2+|b|^2-2ab, topk unsorted) selects the same SET wherever the k-th and
+    # (k+1)-th distances are separated by more than its fp32 cancellation error
+    ref = O.knn_point(k, x, c)
+    d = ((c[:, :, None, :] - x[:, None, :, :]) ** 2).sum(-1)
+    srt = d.sort(dim=-1)[0]
+    clear = (srt[..., k] - srt[..., k - 1] > 1e-5) if k < n else torch.ones(d.shape[:2], dtype=torch.bool)
+    same = (got.sort(-1)[0] == ref.sort(-1)[0]).all(-1)
+    assert bool((same | ~clear).all()) and float(clear.float().mean()) > 0.9
+
+
+def test_cond_silu_matches_time_embedding_path(dev):
+    """table row + per-sample vector -> SiLU -> bf16 must equal what ldt_time_embedding produces with `extra`."""
+    cfg = small_score_cfg()
+    from ldt_b200 import Score
+    m = Score(cfg)
+    m.load_state_dict(O.synth_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 11))
+    m = m.to(dev).eval()
+    P = m.packed()
+    from ldt_b200.sampler import time_embedding_table
+    ts = torch.linspace(1.0, 1e-6, 7, device=dev)
+    table = time_embedding_table(m, P, ts)
+    B = 5
+    extra = torch.randn((B, cfg.t_dim), device=dev)
+    step = torch.tensor([4], dtype=torch.int32, device=dev)
+    c = torch.empty((B, cfg.t_dim), device=dev)
+    sc = torch.empty((B, cfg.t_dim), dtype=torch.bfloat16, device=dev)
+    ops.cond_silu(table, step, extra, c, sc)
+    ws = m._workspace(B, B, dev)
+    m.modulation(P, ws, ts[4].expand(B).contiguous(), extra)
+    assert torch.equal(c, ws.c) and torch.equal(sc, ws.sc)

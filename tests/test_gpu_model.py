@@ -265,3 +265,93 @@ def test_sample_then_decode_end_to_end_small_steps(dev):
     pts = comp.sample((3, 2048), given_eps=eps)
     assert eps.shape == (3, 32, 120) and pts.shape == (3, 2048, 3)
     assert torch.isfinite(eps).all() and torch.isfinite(pts).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# completion path (BASELINE configs[4])
+# ------------------------------------------------------------------------------------------------
+def test_condition_net_and_conditional_score_vs_reference_golden(dev):
+    """Score(condition=True): the ConditionNet prologue (FPS + k-NN kernels, torch layers) against the reference's
+    own outputs, then the conditional forward called with the raw {'img','pts'} dict as the reference allows."""
+    from tests.helpers import small_cond_score_cfg
+    cfg = small_cond_score_cfg()
+    g = golden("condition.npz")
+    model, sd = build_score(cfg, 17, dev)
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False   # fp32 prologue, as the CPU reference
+    try:
+        with torch.no_grad():
+            cond = {"img": g["img"], "pts": g["pts"]}             # CPU tensors: c_net moves them (score.py:34,38)
+            pts_cond, img_cond = model.c_net(cond)
+            out = model(g["x"].to(dev), g["t"].to(dev), condition=cond)
+            out_pts = model(g["x"].to(dev), g["t"].to(dev), condition={"pts": g["pts"]})
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert rel_rms_err(pts_cond, g["pts_cond"]) < 1e-3, rel_rms_err(pts_cond, g["pts_cond"])
+    assert rel_rms_err(img_cond, g["img_cond"]) < 1e-3, rel_rms_err(img_cond, g["img_cond"])
+    check_vs_fp32(out, g["params"])
+    check_vs_fp32(out_pts, g["params_pts_only"])
+
+
+@pytest.mark.parametrize("mode", ["img+pts", "pts", "img", "label"])
+def test_fused_conditional_sampler_equals_stepwise_public_api(dev, mode):
+    """Conditional sampling through the replayed step graph (per-step [B,t_dim] adaLN GEMM from a time-embedding
+    table, condition K/V projected once) == the same loop driven step by step through Score.forward."""
+    from ldt_b200 import DiffusionVPSDE
+    cfg = small_score_cfg()
+    if mode == "label":
+        cfg.num_categorys = 5
+    model, _ = build_score(cfg, 11, dev)
+    sde = DiffusionVPSDE(ns(airplane_config()).sde, device=dev)
+    tr = _Trainer(model, sde)
+    N, B = 10, 6
+    g = torch.Generator().manual_seed(9)
+    tokens = torch.randn((B, cfg.hidden_size, cfg.z_scale), generator=g).to(dev)
+    vec = (0.5 * torch.randn((B, cfg.t_dim), generator=g)).to(dev)
+    label = torch.randint(0, 5, (B,), generator=g).to(dev) if mode == "label" else None
+    condition = {"img+pts": (tokens, vec), "pts": (tokens, 0.0), "img": (None, vec), "label": None}[mode]
+    torch.manual_seed(3); torch.cuda.manual_seed(3)
+    fused = sde.sample_discrete(tr.score_fn, B, N, "ancestral", None, 1, (32, 120), 1e-6, False, True, 0.01, dev,
+                                condition=condition, label=label)
+    torch.manual_seed(3); torch.cuda.manual_seed(3)
+    generic = sde.sample_discrete(lambda t, x, label=None, condition=None: tr.score_fn(t, x, label, condition), B, N,
+                                  "ancestral", None, 1, (32, 120), 1e-6, False, True, 0.01, dev, condition=condition,
+                                  label=label)
+    assert torch.isfinite(fused).all()
+    assert rel_rms_err(fused, generic) < 1e-5, rel_rms_err(fused, generic)
+    # a second run with a different condition reuses the captured graph (buffers refreshed in place)
+    if mode == "img+pts":
+        cond2 = (tokens.flip(0).contiguous(), vec.flip(0).contiguous())
+        torch.manual_seed(3); torch.cuda.manual_seed(3)
+        fused2 = sde.sample_discrete(tr.score_fn, B, N, "ancestral", None, 1, (32, 120), 1e-6, False, True, 0.01, dev,
+                                     condition=cond2)
+        torch.manual_seed(3); torch.cuda.manual_seed(3)
+        generic2 = sde.sample_discrete(lambda t, x, label=None, condition=None: tr.score_fn(t, x, label, condition), B, N,
+                                       "ancestral", None, 1, (32, 120), 1e-6, False, True, 0.01, dev, condition=cond2)
+        assert rel_rms_err(fused2, generic2) < 1e-5
+        assert rel_rms_err(fused2, fused) > 1e-3
+
+
+def test_completion_sample_end_to_end(dev):
+    """completion_trainer/Latent_SDE_Trainer.py:147-170: c_net once, conditional loop, decode."""
+    from ldt_b200 import DiffusionVPSDE
+    from ldt_b200.condition import furthest_point_sample, gather_points
+    from tests.helpers import small_cond_score_cfg
+    c = ns(airplane_config())
+    model, _ = build_score(small_cond_score_cfg(), 17, dev)
+    comp, _ = build_compressor(c.compressor, 13, dev)
+    sde = DiffusionVPSDE(c.sde, device=dev)
+    tr = _Trainer(model, sde)
+    g = torch.Generator().manual_seed(4)
+    B = 4
+    views = torch.rand((B, 3, 64, 64), generator=g)
+    partial = torch.randn((B, 3000, 3), generator=g).to(dev) * 0.3
+    pc_part = gather_points(partial, furthest_point_sample(partial, 2048).long())   # valsample :182-184
+    assert pc_part.shape == (B, 2048, 3)
+    with torch.no_grad():
+        condition = model.c_net({"img": views, "pts": pc_part})
+        torch.manual_seed(0)
+        eps = sde.sample_discrete(tr.score_fn, B, 8, "ancestral", None, 1, (32, 120), 1e-6, False, True, 0.01, dev,
+                                  condition=condition)
+        pts = comp.sample((B, 2048), given_eps=eps)
+    assert pts.shape == (B, 2048, 3) and torch.isfinite(pts).all()
