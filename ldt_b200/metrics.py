@@ -125,3 +125,22 @@ def compute_CD_metrics(sample_pcs, ref_pcs, batch_size=None):
     M_ss_cd = _pairwise_CD_(sample_pcs, sample_pcs, batch_size)
     _update(results, knn(M_rr_cd, M_rs_cd, M_ss_cd, 1, sqrt=False), "CD", only_acc=True)
     return results
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Completion metrics (reference completion_trainer/Latent_SDE_Trainer.py:41-53), on the same NN kernel
+# ------------------------------------------------------------------------------------------------------------------
+def L2_ChamferEval_1000(array1, array2):
+    """1000 * (mean NN distance array1 -> array2 + mean NN distance array2 -> array1) over the whole batch."""
+    dist1, dist2 = distChamferCUDA(array1.float(), array2.float())
+    return (torch.mean(dist1) + torch.mean(dist2)) * 1000
+
+
+def F1Score(array1, array2, threshold=0.001):
+    """(fscore [B], precision_1 [B], precision_2 [B]) at a squared-distance threshold; 0/0 -> 0 as the reference."""
+    dist1, dist2 = distChamferCUDA(array1.float(), array2.float())
+    precision_1 = torch.mean((dist1 < threshold).float(), dim=1)
+    precision_2 = torch.mean((dist2 < threshold).float(), dim=1)
+    fscore = 2 * precision_1 * precision_2 / (precision_1 + precision_2)
+    fscore[torch.isnan(fscore)] = 0
+    return fscore, precision_1, precision_2

@@ -17,6 +17,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
+from ._lib import PRED_CORRECTOR
 from .sde import _PRED_CODES, torch_randn_launch_geometry
 
 
@@ -41,7 +42,7 @@ def modulation_table(score, P, timesteps: torch.Tensor, chunk: int = 256) -> tor
     N = timesteps.shape[0]
     dev = timesteps.device
     half = (score.t_dim // 4) // 2
-    mod_len = score.num_blocks * 6 * score.hidden_size + 2 * score.hidden_size
+    mod_len = score.mod_len
     table = torch.empty((N, mod_len), dtype=torch.float32, device=dev)
     w0, b0, w1, b1 = P["te"]
     for s in range(0, N, chunk):
@@ -71,8 +72,12 @@ class StepGraph:
     """One captured sampler step, replayable; owns the loop state buffers."""
 
     def __init__(self, score, sde, B, N, predictor, time_eps, probability_flow, device, use_graph=True,
-                 per_sample_c=False, cross_attention=False):
+                 per_sample_c=False, cross_attention=False, corrector_steps=0, snr=0.0):
         self.score, self.B, self.N = score, B, N
+        # AncestralCorrector (:212-229): corrector_steps extra (score evaluation + update) pairs per step, each with
+        # its own randn_like draw, so one step consumes 1 + corrector_steps Philox launches' worth of offsets
+        self.corrector_steps = corrector_steps
+        self.ccoef = sde.corrector_coefficients(N, time_eps, snr, device) if corrector_steps > 0 else None
         P = score.packed()
         self.P = P
         self.coef, self.timesteps = sde.step_coefficients(predictor, N, time_eps, probability_flow, device)
@@ -126,19 +131,30 @@ class StepGraph:
             mod, mod_stride = self.mod_cur, 0
         self.score.run_tokens(self.P, self.ws, self.x.view(B * T, D), mod, mod_stride, self.params.view(B * T, D),
                               self.kv_cond)
+        draws = 1 + self.corrector_steps
         ops.sde_step(self.code, self.x, self.params, None, self.coef, self.step, self.seed, self.offset,
-                     self.offset_per_step, self.rng_grid, self.x, self.x_mean)
+                     draws * self.offset_per_step, self.rng_grid, self.x, self.x_mean)
+        for j in range(self.corrector_steps):
+            self.score.run_tokens(self.P, self.ws, self.x.view(B * T, D), mod, mod_stride, self.params.view(B * T, D),
+                                  self.kv_cond)
+            ops.sde_step(PRED_CORRECTOR, self.x, self.params, None, self.ccoef, self.step, self.seed,
+                         self.offset + (1 + j) * self.offset_per_step, draws * self.offset_per_step, self.rng_grid,
+                         self.x, self.x_mean)
         ops.advance_step(self.step)
 
-    def run(self, x0: torch.Tensor, seed: int, offset: int) -> None:
-        """Run all N steps from x0 (copied into the loop buffer) with Philox (seed, offset)."""
+    def run(self, x0: torch.Tensor, seed: int, offset: int, record_every: int | None = None) -> list:
+        """Run all N steps from x0 (copied into the loop buffer) with Philox (seed, offset).  With record_every = s
+        returns the x_mean snapshots after steps s, 2s, ... (the print_steps trajectory, :239-257)."""
         self.x.copy_(x0)
         self.step.zero_()
+        snaps = []
         if not self.use_graph:
             self.seed, self.offset = seed, offset
-            for _ in range(self.N):
+            for i in range(self.N):
                 self._step_body()
-            return
+                if record_every and (i + 1) % record_every == 0:
+                    snaps.append(self.x_mean.clone())
+            return snaps
         if self.graph is None or (seed, offset) != (self.seed, self.offset):
             # seed/offset are baked into the captured kernel arguments: (re)capture for a new generator position
             self.seed, self.offset = seed, offset
@@ -154,16 +170,19 @@ class StepGraph:
             ops.add_launches(-self.launches_per_step)  # captured, not executed
             self.graph = g
             # the capture itself does not execute; state is still (x0, step 0)
-        for _ in range(self.N):
+        for i in range(self.N):
             self.graph.replay()
+            if record_every and (i + 1) % record_every == 0:
+                snaps.append(self.x_mean.clone())
         ops.add_launches(self.N * self.launches_per_step)
+        return snaps
 
 
 _graph_cache: dict = {}
 
 
 def fused_sample_loop(score, sde, x0, N, predictor, time_eps, probability_flow, denoise, use_graph=True,
-                      cond_tokens=None, extra=None):
+                      cond_tokens=None, extra=None, print_steps=None, corrector_steps=0, snr=0.0):
     """x0 [B, z_scale, z_dim] on the device -> latent after N reverse steps (x_mean if denoise else x).
 
     cond_tokens [B, hidden, z_scale] (condition[0], cross-attended by the even blocks) and extra [B, t_dim]
@@ -172,18 +191,23 @@ def fused_sample_loop(score, sde, x0, N, predictor, time_eps, probability_flow, 
     B = x0.shape[0]
     per_sample_c, cross = extra is not None, cond_tokens is not None
     key = (id(score), id(sde), B, N, predictor, float(time_eps), bool(probability_flow), device, use_graph,
-           per_sample_c, cross, score._fingerprint())
+           per_sample_c, cross, corrector_steps, float(snr), score._fingerprint())
     sg = _graph_cache.get(key)
     if sg is None:
         _graph_cache.clear()  # one live plan: the buffers are large (modulation table ~0.6 GB at N=1000)
         sg = StepGraph(score, sde, B, N, predictor, time_eps, probability_flow, device, use_graph,
-                       per_sample_c=per_sample_c, cross_attention=cross)
+                       per_sample_c=per_sample_c, cross_attention=cross, corrector_steps=corrector_steps, snr=snr)
         _graph_cache[key] = sg
     if per_sample_c or cross:
         sg.set_condition(cond_tokens, extra)
     gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
     seed, offset = gen.initial_seed(), gen.get_offset()
-    sg.run(x0, seed, offset)
-    # the reference draws one randn_like per step from this generator (:160); leave it where it would be
-    gen.set_offset(offset + N * sg.offset_per_step)
-    return (sg.x_mean if denoise else sg.x).clone()
+    record_every = (N - 1) // (print_steps - 2) if print_steps is not None else None
+    snaps = sg.run(x0, seed, offset, record_every)
+    # the reference draws one randn_like per predictor / corrector update from this generator (:160,204,224); leave it
+    # where it would be
+    gen.set_offset(offset + N * (1 + corrector_steps) * sg.offset_per_step)
+    final = (sg.x_mean if denoise else sg.x).clone()
+    if print_steps is not None:
+        return [x0] + snaps + [final]
+    return final

@@ -46,6 +46,23 @@ class _AdaLNBlockParams(nn.Module):
         self.mlp = _MLPParams(dim, int(mlp_ratio * dim))
 
 
+class _AdaLNDownBlockParams(nn.Module):
+    """Parameter holder for a UNet "Down" ResidualBlock, dim_in = 2*dim_out (model/layers.py:153-155,173-175): the
+    concatenated [x | skip] stream is normalised over 2*dim channels, projected to dim-wide q/k/v, and enters the
+    residual through a Conv1d(2*dim -> dim) shortcut; adaLN1 -> (shift, scale) of the 2*dim norm, adaLN2 -> the gates
+    and the MLP modulation."""
+
+    def __init__(self, dim, dim_c, mlp_ratio=4.0):
+        super().__init__()
+        self.shortcut = nn.Conv1d(2 * dim, dim, 1)
+        self.fc_q = nn.Conv1d(2 * dim, dim, 1)
+        self.fc_kv = nn.Conv1d(2 * dim, 2 * dim, 1)
+        self.fc_o = nn.Conv1d(dim, dim, 1)
+        self.adaLN1 = nn.Sequential(nn.SiLU(), nn.Linear(dim_c, 4 * dim))
+        self.adaLN2 = nn.Sequential(nn.SiLU(), nn.Linear(dim_c, 4 * dim))
+        self.mlp = _MLPParams(dim, int(mlp_ratio * dim))
+
+
 class _TimeEmbeddingParams(nn.Module):
     def __init__(self, dim_embed, dim_out):
         super().__init__()
@@ -77,11 +94,18 @@ def _pad_to(n: int, g: int) -> int:
 class _Workspace:
     """Caller-owned device buffers for one batch size (the kernels never allocate)."""
 
-    def __init__(self, B, tokens, z_dim, hidden, n_blocks, mod_rows, half, device, t_dim=None):
+    def __init__(self, B, tokens, z_dim, hidden, n_blocks, mod_rows, half, device, t_dim=None, mod_len=None,
+                 unet_skips=0):
         M = B * tokens
         bf, f32 = torch.bfloat16, torch.float32
         self.B, self.M = B, M
-        self.mod_len = n_blocks * 6 * hidden + 2 * hidden
+        self.mod_len = n_blocks * 6 * hidden + 2 * hidden if mod_len is None else mod_len
+        if unet_skips:   # UNet variant: saved Up outputs, the [x | skip] stream (fp32 and bf16) and the shortcut output
+            self.skips = [torch.empty((M, hidden), dtype=f32, device=device) for _ in range(unet_skips)]
+            self.hcat = torch.empty((M, 2 * hidden), dtype=f32, device=device)
+            self.acat = torch.empty((M, 2 * hidden), dtype=bf, device=device)
+            self.ccat = torch.empty((M, 2 * hidden), dtype=bf, device=device)
+            self.hsc = torch.empty((M, hidden), dtype=f32, device=device)
         self.xa = torch.zeros((M, _pad_to(z_dim, 64)), dtype=bf, device=device)
         self.h = torch.empty((M, hidden), dtype=f32, device=device)
         self.a = torch.empty((M, hidden), dtype=bf, device=device)
@@ -118,8 +142,6 @@ class Score(nn.Module):
         self.learn_sigma = cfg.learn_sigma
         self.unet = cfg.unet
         self.AdaLN = cfg.AdaLN
-        if self.unet:
-            raise NotImplementedError("ldt_b200.Score: the unet variant (score.py:67-83) is not on the B200 hot path yet")
         if not self.AdaLN:
             raise NotImplementedError("ldt_b200.Score: only AdaLN blocks (the shipped configs) are supported")
         if self.norm != "layer_norm":
@@ -133,8 +155,15 @@ class Score(nn.Module):
         if self.condition:
             from .condition import ConditionNet
             self.c_net = ConditionNet(self.hidden_size, self.t_dim, patch_size=self.z_scale)
-        self.Transformer = nn.ModuleList(
-            [_AdaLNBlockParams(self.hidden_size, self.hidden_size, self.t_dim) for _ in range(self.num_blocks)])
+        if self.unet:   # score.py:67-83: num_blocks//2 Up blocks, one Mid block, num_blocks//2 Down blocks on [x | skip]
+            self.Transformer_Up = nn.ModuleList(
+                [_AdaLNBlockParams(self.hidden_size, self.hidden_size, self.t_dim) for _ in range(self.num_blocks // 2)])
+            self.Transformer_Mid = _AdaLNBlockParams(self.hidden_size, self.hidden_size, self.t_dim)
+            self.Transformer_Down = nn.ModuleList(
+                [_AdaLNDownBlockParams(self.hidden_size, self.t_dim) for _ in range(self.num_blocks // 2)])
+        else:
+            self.Transformer = nn.ModuleList(
+                [_AdaLNBlockParams(self.hidden_size, self.hidden_size, self.t_dim) for _ in range(self.num_blocks)])
         if cfg.num_categorys > 1:
             self.LabelEmbedding = _LabelEmbeddingParams(cfg.num_categorys, self.t_dim, self.t_dim)
         else:
@@ -174,28 +203,39 @@ class Score(nn.Module):
             P["b_in"] = self.ln_in.bias.detach().float().contiguous()
             P["blocks"] = []
             ada_w, ada_b = [], []
-            for blk in self.Transformer:
-                wq = torch.cat([blk.fc_q.weight.detach().reshape(self.hidden_size, -1),
-                                blk.fc_kv.weight.detach().reshape(2 * self.hidden_size, -1)], dim=0)
-                # head-major packing for the fused projection+attention kernel: [q_h | k_h | v_h] per head
-                dh = self.hidden_size // self.num_heads
-                Hn, Hd = self.num_heads, self.hidden_size
-                perm = torch.stack([torch.arange(Hn).view(Hn, 1) * dh + torch.arange(dh).view(1, dh) + off
-                                    for off in (0, Hd, 2 * Hd)], dim=1).reshape(-1).to(wq.device)
+            Hn, Hd = self.num_heads, self.hidden_size
+            dh = Hd // Hn
+            # head-major packing for the fused projection+attention kernel: [q_h | k_h | v_h] per head
+            perm = torch.stack([torch.arange(Hn).view(Hn, 1) * dh + torch.arange(dh).view(1, dh) + off
+                                for off in (0, Hd, 2 * Hd)], dim=1).reshape(-1).to(dev)
+
+            def pack_block(blk):
+                wq = torch.cat([blk.fc_q.weight.detach().reshape(Hd, -1), blk.fc_kv.weight.detach().reshape(2 * Hd, -1)], dim=0)
                 bq = torch.cat([blk.fc_q.bias.detach(), blk.fc_kv.bias.detach()]).float()
-                d = {
+                return {
                     "w_qkv_p": ops.pack_weight(wq[perm]) if dh == 64 else None,
                     "b_qkv_p": bq[perm].contiguous() if dh == 64 else None,
                     "w_qkv": ops.pack_weight(wq),
-                    "b_qkv": torch.cat([blk.fc_q.bias.detach(), blk.fc_kv.bias.detach()]).float().contiguous(),
+                    "b_qkv": bq.contiguous(),
                     "w_o": ops.pack_weight(blk.fc_o.weight), "b_o": blk.fc_o.bias.detach().float().contiguous(),
                     "w_fc1": ops.pack_weight(blk.mlp.fc[0][0].weight),
                     "b_fc1": blk.mlp.fc[0][0].bias.detach().float().contiguous(),
                     "w_fc2": ops.pack_weight(blk.mlp.out.weight), "b_fc2": blk.mlp.out.bias.detach().float().contiguous(),
                 }
-                P["blocks"].append(d)
+
+            plain = list(self.Transformer_Up) + [self.Transformer_Mid] if self.unet else list(self.Transformer)
+            for blk in plain:
+                P["blocks"].append(pack_block(blk))
                 ada_w.append(blk.adaLN[1].weight.detach())
                 ada_b.append(blk.adaLN[1].bias.detach())
+            P["down"] = []
+            for blk in (self.Transformer_Down if self.unet else []):
+                d = pack_block(blk)
+                d["w_sc"] = ops.pack_weight(blk.shortcut.weight)
+                d["b_sc"] = blk.shortcut.bias.detach().float().contiguous()
+                P["down"].append(d)
+                ada_w += [blk.adaLN1[1].weight.detach(), blk.adaLN2[1].weight.detach()]
+                ada_b += [blk.adaLN1[1].bias.detach(), blk.adaLN2[1].bias.detach()]
             ada_w.append(self.ln_out.adaLN[1].weight.detach())
             ada_b.append(self.ln_out.adaLN[1].bias.detach())
             P["w_ada"] = ops.pack_weight(torch.cat(ada_w, dim=0))
@@ -210,11 +250,21 @@ class Score(nn.Module):
         self._packed, self._packed_key = P, key
         return P
 
+    @property
+    def mod_len(self) -> int:
+        """Width of one row of concatenated adaLN outputs: 6H per plain block, 8H per Down block, 2H for ln_out."""
+        H = self.hidden_size
+        if self.unet:
+            n = self.num_blocks // 2
+            return (n + 1) * 6 * H + n * 8 * H + 2 * H
+        return self.num_blocks * 6 * H + 2 * H
+
     def _workspace(self, B, mod_rows, device):
         half = (self.t_dim // 4) // 2
         ws = self._ws.get(B)
         if ws is None or ws.h.device != device:
-            ws = _Workspace(B, self.z_scale, self.z_dim, self.hidden_size, self.num_blocks, mod_rows, half, device, self.t_dim)
+            ws = _Workspace(B, self.z_scale, self.z_dim, self.hidden_size, self.num_blocks, mod_rows, half, device, self.t_dim,
+                            mod_len=self.mod_len, unet_skips=(self.num_blocks // 2 if self.unet else 0))
             self._ws[B] = ws
         elif ws.R != mod_rows:
             ws.set_mod_rows(mod_rows, self.hidden_size, half, device)
@@ -235,6 +285,8 @@ class Score(nn.Module):
     def run_tokens(self, P, ws, x_tokens, mod, mod_stride, out, kv_cond=None):
         """The per-step token path: x_tokens f32 [M, z_dim] -> out f32 [M, z_dim].  ``mod`` holds the AdaLN
         rows (one row broadcast when mod_stride == 0, else one per sample)."""
+        if self.unet:
+            return self._run_tokens_unet(P, ws, x_tokens, mod, mod_stride, out, kv_cond)
         Hd, T = self.hidden_size, self.z_scale
         B = ws.B
         heads, dh = self.num_heads, Hd // self.num_heads
@@ -269,6 +321,66 @@ class Score(nn.Module):
             ops.gemm(ws.hid, W["w_fc2"], W["b_fc2"], ws.h, EPI_GATE_RESID_F32, resid=ws.h, gate=mview(base + 5 * Hd),
                      gate_stride=mod_stride, rows_per_gate=T)
         base = self.num_blocks * 6 * Hd
+        ops.layernorm_mod(ws.h, ws.a, shift=mview(base), scale=mview(base + Hd), mod_stride=mod_stride, rows_per_mod=T)
+        ops.gemm(ws.a, P["w_out"], P["b_out"], out, EPI_BIAS_F32, N=self.z_dim)
+        return out
+
+    def _run_tokens_unet(self, P, ws, x_tokens, mod, mod_stride, out, kv_cond=None):
+        """UNet wiring of score.py:138-146: Up blocks (outputs saved), Mid, then Down blocks on cat(x, saved.pop())."""
+        if kv_cond is not None:
+            raise NotImplementedError(
+                "unet score net with condition tokens: the reference's Down blocks (dim_kv = 2*hidden) cannot attend "
+                "to hidden-wide condition tokens either (score.py:143-146)")
+        Hd, T, B = self.hidden_size, self.z_scale, ws.B
+        heads, dh = self.num_heads, Hd // self.num_heads
+        mp = mod.data_ptr()
+        q = ws.qkv
+        k = _PtrView(ws.qkv.data_ptr() + 2 * Hd)
+        v = _PtrView(ws.qkv.data_ptr() + 4 * Hd)
+
+        def mview(off):
+            return _PtrView(mp + 4 * off)
+
+        def attention(a, W):
+            if self.fused_attention and W["w_qkv_p"] is not None:
+                ops.qkv_attention(B, heads, a, W["w_qkv_p"], W["b_qkv_p"], ws.att)
+            else:
+                ops.gemm(a, W["w_qkv"], W["b_qkv"], ws.qkv, EPI_BIAS_BF16)
+                ops.attention_nk32(B, heads, T, dh, q, 3 * Hd, k, v, 3 * Hd, ws.att)
+
+        def mlp_half(W, base_shift, base_scale, base_gate):
+            ops.layernorm_mod(ws.h, ws.a, shift=mview(base_shift), scale=mview(base_scale), mod_stride=mod_stride, rows_per_mod=T)
+            ops.gemm(ws.a, W["w_fc1"], W["b_fc1"], ws.hid, EPI_BIAS_GELU_BF16)
+            ops.gemm(ws.hid, W["w_fc2"], W["b_fc2"], ws.h, EPI_GATE_RESID_F32, resid=ws.h, gate=mview(base_gate),
+                     gate_stride=mod_stride, rows_per_gate=T)
+
+        ops.cast_pad_bf16(x_tokens, ws.xa.shape[1], out=ws.xa)
+        ops.gemm(ws.xa, P["w_in"], P["b_in"], ws.h, EPI_BIAS_F32)
+        n = self.num_blocks // 2
+        base = 0
+        for i, W in enumerate(P["blocks"]):      # n Up blocks then the Mid block, all plain AdaLN blocks
+            ops.layernorm_mod(ws.h, ws.a, shift=mview(base), scale=mview(base + Hd), mod_stride=mod_stride, rows_per_mod=T)
+            attention(ws.a, W)
+            ops.gemm(ws.att, W["w_o"], W["b_o"], ws.h, EPI_GATE_RESID_F32, resid=ws.h, gate=mview(base + 2 * Hd),
+                     gate_stride=mod_stride, rows_per_gate=T)
+            mlp_half(W, base + 3 * Hd, base + 4 * Hd, base + 5 * Hd)
+            if i < n:
+                ws.skips[i].copy_(ws.h)          # x_list.append(x)  (:141)
+            base += 6 * Hd
+        for j, W in enumerate(P["down"]):
+            # x = cat(x, x_list.pop()) on channels (:145); adaLN1 -> (shift, scale) [2H each], adaLN2 -> (gate_msa,
+            # shift_mlp, scale_mlp, gate_mlp) [H each]  (layers.py:216-217)
+            ws.hcat[:, :Hd].copy_(ws.h)
+            ws.hcat[:, Hd:].copy_(ws.skips[n - 1 - j])
+            ops.layernorm_mod(ws.hcat, ws.acat, shift=mview(base), scale=mview(base + 2 * Hd), mod_stride=mod_stride,
+                              rows_per_mod=T)
+            attention(ws.acat, W)
+            ops.cast_pad_bf16(ws.hcat, 2 * Hd, out=ws.ccat)
+            ops.gemm(ws.ccat, W["w_sc"], W["b_sc"], ws.hsc, EPI_BIAS_F32)                      # shortcut(x)
+            ops.gemm(ws.att, W["w_o"], W["b_o"], ws.h, EPI_GATE_RESID_F32, resid=ws.hsc, gate=mview(base + 4 * Hd),
+                     gate_stride=mod_stride, rows_per_gate=T)
+            mlp_half(W, base + 5 * Hd, base + 6 * Hd, base + 7 * Hd)
+            base += 8 * Hd
         ops.layernorm_mod(ws.h, ws.a, shift=mview(base), scale=mview(base + Hd), mod_stride=mod_stride, rows_per_mod=T)
         ops.gemm(ws.a, P["w_out"], P["b_out"], out, EPI_BIAS_F32, N=self.z_dim)
         return out

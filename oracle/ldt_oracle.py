@@ -110,6 +110,42 @@ def residual_block_adaln(sd, prefix, x, y, c, num_heads):
     return x + gate_mlp * mlp(sd, prefix + "mlp.", h)
 
 
+def residual_block_adaln_down(sd, prefix, x, y, c, num_heads):
+    """ResidualBlock.forward, AdaLN branch with dim_in = 2*dim_out (UNet Down blocks): model/layers.py:153-155,
+    173-175, 216-219 -- Conv1d shortcut on the raw input, adaLN1 -> (shift, scale) of the dim_in-wide norm, adaLN2 ->
+    (gate_msa, shift_mlp, scale_mlp, gate_mlp)."""
+    cc = c[:, None, :] if c.dim() == 2 else c.transpose(1, 2)
+    m1 = F.linear(_q(F.silu(cc)), _q(sd[prefix + "adaLN1.1.weight"]), sd[prefix + "adaLN1.1.bias"]).transpose(1, 2)
+    m2 = F.linear(_q(F.silu(cc)), _q(sd[prefix + "adaLN2.1.weight"]), sd[prefix + "adaLN2.1.bias"]).transpose(1, 2)
+    shift_msa, scale_msa = m1.chunk(2, dim=1)
+    gate_msa, shift_mlp, scale_mlp, gate_mlp = m2.chunk(4, dim=1)
+    h = layer_norm_cf(x) * (1 + scale_msa) + shift_msa
+    x = conv1x1(x, sd[prefix + "shortcut.weight"], sd[prefix + "shortcut.bias"]) + gate_msa * attention(sd, prefix, h, y, num_heads)
+    h = layer_norm_cf(x) * (1 + scale_mlp) + shift_mlp
+    return x + gate_mlp * mlp(sd, prefix + "mlp.", h)
+
+
+def score_forward_unet(sd, cfg, x, t, cond_vec=None):
+    """Score.forward with ``unet: True`` (model/scorenet/score.py:138-146), unconditional or image-vector only."""
+    c = time_embedding(sd, t.to(x.dtype))
+    if cond_vec is not None:
+        c = c + cond_vec
+    h = conv1x1(x.transpose(1, 2), sd["ln_in.weight"], sd["ln_in.bias"])
+    n = cfg.num_blocks // 2
+    saved = [h]
+    for i in range(n):
+        h = residual_block_adaln(sd, f"Transformer_Up.{i}.", h, None, c, cfg.num_heads)
+        saved.append(h)
+    h = residual_block_adaln(sd, "Transformer_Mid.", h, None, c, cfg.num_heads)
+    for i in range(n):
+        h = torch.cat((h, saved.pop()), dim=1)
+        h = residual_block_adaln_down(sd, f"Transformer_Down.{i}.", h, None, c, cfg.num_heads)
+    mod = F.linear(_q(F.silu(c[:, None, :])), _q(sd["ln_out.adaLN.1.weight"]), sd["ln_out.adaLN.1.bias"]).transpose(1, 2)
+    shift, scale = mod.chunk(2, dim=1)
+    h = layer_norm_cf(h) * (1 + scale) + shift
+    return conv1x1(h, sd["ln_out.ln.weight"], sd["ln_out.ln.bias"]).transpose(1, 2)
+
+
 def residual_block_plain(sd, prefix, x, y, num_heads):
     """ResidualBlock.forward with c=None and act=Identity (decoder): model/layers.py:224-226."""
     h = layer_norm_cf(x, sd[prefix + "norm1.norm.weight"], sd[prefix + "norm1.norm.bias"])
@@ -242,30 +278,100 @@ def ddim_step(sde, x, t, params, N):
     return x_mean, x_mean
 
 
-def sample_discrete(sde, score_net, x0, N, time_eps, noises, predictor="ancestral", denoise=True):
-    """pc_sampling loop, :231-258, with the per-step noise supplied by the caller (noises[i] ~ randn_like)."""
+def ancestral_corrector_step(sde, x, t, params, noise, snr):
+    """AncestralCorrector, :212-229.  alpha = 1: `self.__class__ in ["DiffusionVPSDE", ...]` is never true."""
+    grad = score_from_params(sde, params, t)
+    alpha = torch.ones_like(t)
+    step_size = (snr * torch.sqrt(sde.var(t))) ** 2 * 2 * alpha
+    x_mean = x + step_size[:, None, None] * grad
+    return x_mean + noise * torch.sqrt(step_size * 2)[:, None, None], x_mean
+
+
+def langevin_corrector_step(sde, x, t, params, noise, snr):
+    """LangevinCorrector, :193-210, with the scalar the reference's `step_size[:, None]` broadcast stands for."""
+    grad = score_from_params(sde, params, t)
+    grad_norm = torch.norm(grad.reshape(grad.shape[0], -1), dim=-1).mean()
+    noise_norm = torch.norm(noise.reshape(noise.shape[0], -1), dim=-1).mean()
+    step_size = (snr * noise_norm / grad_norm) ** 2 * 2
+    x_mean = x + step_size * grad
+    return x_mean + torch.sqrt(step_size * 2) * noise, x_mean
+
+
+def sample_discrete(sde, score_net, x0, N, time_eps, noises, predictor="ancestral", denoise=True, corrector=None,
+                    corrector_steps=1, snr=0.01, print_steps=None):
+    """pc_sampling loop, :231-258, with the noise supplied by the caller in draw order (noises[j] ~ randn_like)."""
     x = x0
     timesteps = torch.linspace(1.0, time_eps, N)
     x_mean = x
+    it = iter(noises)
+    out_list = [x] if print_steps is not None else None
+    steps = (N - 1) // (print_steps - 2) if print_steps is not None else None
     for i in range(N):
         vec_t = torch.ones((x.shape[0],)) * timesteps[i]
-        params = score_net(x, vec_t)
-        if predictor == "ancestral":
-            x, x_mean = ancestral_step(sde, x, vec_t, params, noises[i], N)
-        elif predictor == "reversediffusion":
-            x, x_mean = reverse_diffusion_step(sde, x, vec_t, params, noises[i], N, time_eps)
-        elif predictor == "eulermaruyama":
-            x, x_mean = euler_maruyama_step(sde, x, vec_t, params, noises[i], N)
-        elif predictor == "ddim":
-            x, x_mean = ddim_step(sde, x, vec_t, params, N)
-        else:
-            raise NotImplementedError(predictor)
+        x_mean = x
+        if predictor is not None:
+            params = score_net(x, vec_t)
+            if predictor == "ancestral":
+                x, x_mean = ancestral_step(sde, x, vec_t, params, next(it), N)
+            elif predictor == "reversediffusion":
+                x, x_mean = reverse_diffusion_step(sde, x, vec_t, params, next(it), N, time_eps)
+            elif predictor == "eulermaruyama":
+                x, x_mean = euler_maruyama_step(sde, x, vec_t, params, next(it), N)
+            elif predictor == "ddim":
+                next(it)  # DDIM draws a noise it multiplies by sigma = 0 (:178-179)
+                x, x_mean = ddim_step(sde, x, vec_t, params, N)
+            else:
+                raise NotImplementedError(predictor)
+        if corrector is not None:
+            for _ in range(corrector_steps):
+                params = score_net(x, vec_t)
+                fn = {"ancestral": ancestral_corrector_step, "langevin": langevin_corrector_step}[corrector]
+                x, x_mean = fn(sde, x, vec_t, params, next(it), snr)
+        if out_list is not None and (i + 1) % steps == 0:
+            out_list.append(x_mean)
+    if out_list is not None:
+        out_list.append(x_mean if denoise else x)
+        return out_list
     return x_mean if denoise else x
 
 
-# --------------------------------------------------------------------------------------------------
-# Chamfer / metrics (evaluation/evaluation_metrics.py)
-# --------------------------------------------------------------------------------------------------
+def pndm_sample(sde, score_net, x0, sample_N, train_N, time_eps):
+    """predictor == "pndm", :260-316: Runge-Kutta warm-up for the first three steps, then 4-term linear multistep.
+    Index arithmetic as written in the reference (timesteps[-1] on the last step included)."""
+    timesteps = torch.linspace(time_eps, 1.0, sample_N * 2)
+    betas = torch.from_numpy(np.linspace(sde.beta_start / train_N, sde.beta_end / train_N, train_N, dtype=np.float64)).float()
+    alphas_cump = torch.cat((torch.ones(1), (1.0 - betas).cumprod(dim=0)))
+    B = x0.shape[0]
+
+    def tv(i):
+        return timesteps[i].view(-1).expand(B).to(x0)
+
+    def transfer(x, t, t_next, et):
+        at = alphas_cump[(train_N * (t - time_eps) + 1).long()][0]
+        at_next = alphas_cump[(train_N * (t_next - time_eps) + 1).long()][0]
+        x_delta = (at_next - at) * ((1 / (at.sqrt() * (at.sqrt() + at_next.sqrt()))) * x - 1 / (at.sqrt() * (
+            ((1 - at_next) * at).sqrt() + ((1 - at) * at_next).sqrt())) * et)
+        return x + x_delta
+
+    x, ets = x0, []
+    for idx in range(sample_N, 0, -1):
+        t_next = idx - 1
+        t_list = [idx, (idx + t_next) / 2, t_next]
+        if len(ets) > 2:
+            ets.append(score_net(x, tv(idx * 2 - 1)))
+            noise = (1 / 24) * (55 * ets[-1] - 59 * ets[-2] + 37 * ets[-3] - 9 * ets[-4])
+        else:
+            t1, t2, t3 = tv(t_list[0] * 2 - 1), tv(int(t_list[1] * 2) - 1), tv(int(t_list[2] * 2) - 1)
+            e1 = score_net(x, t1)
+            ets.append(e1)
+            e2 = score_net(transfer(x, t1, t2, e1), t2)
+            e3 = score_net(transfer(x, t1, t2, e2), t2)
+            e4 = score_net(transfer(x, t1, t3, e3), t3)
+            noise = (1 / 6) * (e1 + 2 * e2 + 2 * e3 + e4)
+        x = transfer(x, tv(idx * 2 - 1), tv(t_next * 2 - 1), noise)
+    return x
+
+
 def nn_distance_f64(a, b):
     """ChamferDistancePytorch/chamfer_python.py:18-39 style brute force in float64 (the check of
     unit_test.py:22-33): returns dist1, idx1, dist2, idx2."""

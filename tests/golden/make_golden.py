@@ -96,6 +96,24 @@ def gen_score():
         del model
 
 
+def gen_unet():
+    """The UNet wiring of the score net (score.py:67-83,138-146; default of model/scorenet/config.yaml)."""
+    from model.scorenet.score import Score
+    from tests.helpers import small_unet_score_cfg
+    cfg = small_unet_score_cfg()
+    torch.manual_seed(0)
+    model = Score(cfg).eval()
+    load_synth(model, 19)
+    g = torch.Generator().manual_seed(119)
+    x = torch.randn((3, cfg.z_scale, cfg.z_dim), generator=g)
+    t = torch.rand((3,), generator=g) * 0.98 + 0.01
+    img_cond = torch.randn((3, cfg.t_dim), generator=g) * 0.5
+    with torch.no_grad():
+        params = model(x, t)
+        params_c = model(x, t, condition=(None, img_cond))
+    save("score_unet.npz", x=x, t=t, img_cond=img_cond, params=params, params_cond=params_c)
+
+
 def gen_condition():
     """ConditionNet + conditional Score from the reference, with the un-vendored pointnet2_ops FPS replaced by the C
     oracle (oracle/pointops_oracle.c); the same stand-in is used by the oracle-vs-golden test."""
@@ -179,6 +197,46 @@ def gen_sde():
                     out[f"{pred}_noise"] = torch.stack(noises)
         save("sde.npz", **out)
 
+        # correctors, print_steps trajectory and PNDM.  The reference's `step_size[:, None]` /
+        # `at.view(-1, 1)` broadcasts only type-check when the batch equals shape[0] (or 1): batch 32, shape (32, 4).
+        ext = {}
+
+        def run(tag, sde_obj=sde, **kw):
+            noises = []
+
+            def rec(x, *a, **k):
+                z = real_randn_like(x, *a, **k)
+                noises.append(z.clone())
+                return z
+
+            def score_fn(t, x, label=None, condition=None):
+                params = 0.3 * x + torch.sin(5.0 * t)[:, None, None]
+                return -params / torch.sqrt(sde_obj.var(t))[:, None, None], params
+
+            args = dict(score_fn=score_fn, num_samples=32, N=5, predictor="ancestral", corrector=None, corrector_steps=1,
+                        shape=(32, 4), time_eps=1e-6, probability_flow=False, denoise=True, snr=0.16, device="cpu")
+            args.update(kw)
+            torch.manual_seed(33)
+            torch.randn_like = rec
+            try:
+                res = sde_obj.sample_discrete(**args)
+            finally:
+                torch.randn_like = real_randn_like
+            torch.manual_seed(33)
+            ext[f"{tag}_x0"] = torch.randn((32, 32, 4))
+            ext[f"{tag}_out"] = torch.stack(res) if isinstance(res, list) else res
+            if noises:
+                ext[f"{tag}_noise"] = torch.stack(noises)
+
+        run("pc_ancestral", corrector="ancestral", corrector_steps=2)
+        run("pc_langevin", corrector="langevin", corrector_steps=1, predictor="eulermaruyama")
+        run("c_only_ancestral", predictor=None, corrector="ancestral", corrector_steps=1, denoise=False)
+        run("print_steps", print_steps=4)
+        cfg2 = dict2namespace(airplane_config()).sde
+        cfg2.sample_N = 6
+        run("pndm", sde_obj=DiffusionVPSDE(cfg2), predictor="pndm")
+        save("sde_ext.npz", **ext)
+
 
 def gen_layout():
     """state_dict key -> shape of the reference modules for the shipped config (the checkpoint contract)."""
@@ -187,8 +245,9 @@ def gen_layout():
     from model.scorenet.score import Score
     cfg = dict2namespace(airplane_config())
     cfg.score.num_blocks = 2  # layout per block is identical; keeps the instantiation light
-    from tests.helpers import small_cond_score_cfg
-    lay = {"score_cond_small": [[k, list(v.shape)] for k, v in Score(small_cond_score_cfg()).state_dict().items()],
+    from tests.helpers import small_cond_score_cfg, small_unet_score_cfg
+    lay = {"score_unet_small": [[k, list(v.shape)] for k, v in Score(small_unet_score_cfg()).state_dict().items()],
+           "score_cond_small": [[k, list(v.shape)] for k, v in Score(small_cond_score_cfg()).state_dict().items()],
            "score_2blocks": [[k, list(v.shape)] for k, v in Score(cfg.score).state_dict().items()],
            "compressor": [[k, list(v.shape)] for k, v in Compressor(cfg.compressor).state_dict().items()]}
     with open(os.path.join(HERE, "state_dict_layout.json"), "w") as f:
@@ -222,6 +281,6 @@ def gen_nn():
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 1)
-    which = sys.argv[1:] or ["score", "condition", "decoder", "sde", "nn", "layout"]
+    which = sys.argv[1:] or ["score", "unet", "condition", "decoder", "sde", "nn", "layout"]
     for w in which:
-        {"score": gen_score, "condition": gen_condition, "decoder": gen_decoder, "sde": gen_sde, "nn": gen_nn, "layout": gen_layout}[w]()
+        {"score": gen_score, "unet": gen_unet, "condition": gen_condition, "decoder": gen_decoder, "sde": gen_sde, "nn": gen_nn, "layout": gen_layout}[w]()

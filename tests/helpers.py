@@ -101,3 +101,11 @@ def small_cond_score_cfg() -> SimpleNamespace:
     c = small_score_cfg()
     c.condition = True
     return c
+
+
+def small_unet_score_cfg() -> SimpleNamespace:
+    """Reduced UNet score config (``unet: True`` is the default of the reference's model/scorenet/config.yaml)."""
+    c = small_score_cfg()
+    c.unet = True
+    c.num_blocks = 4
+    return c

@@ -75,9 +75,12 @@ def test_config_validation_mirrors_reference_errors():
     with pytest.raises(AttributeError):
         Score(cfg.score)
     cfg = ns(airplane_config())
-    cfg.score.unet = True
+    cfg.score.AdaLN = False   # only the AdaLN blocks of the shipped configs are built
     with pytest.raises(NotImplementedError):
         Score(cfg.score)
+    cfg = ns(airplane_config())
+    cfg.score.unet, cfg.score.num_blocks, cfg.score.hidden_size, cfg.score.num_heads = True, 2, 128, 2
+    assert any(k.startswith("Transformer_Down.0.adaLN2.1.") for k in Score(cfg.score).state_dict())
     sde = DiffusionVPSDE(cfg.sde, device="cpu")
     assert sde.betas.dtype == torch.float32 and sde.betas.shape == (1000,)
     with pytest.raises(NotImplementedError, match="preditor not Implemented"):  # message of diffusion_continuous.py:327

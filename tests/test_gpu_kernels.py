@@ -524,3 +524,23 @@ def test_cond_silu_matches_time_embedding_path(dev):
     ws = m._workspace(B, B, dev)
     m.modulation(P, ws, ts[4].expand(B).contiguous(), extra)
     assert torch.equal(c, ws.c) and torch.equal(sc, ws.sc)
+
+
+def test_completion_metrics_chamfer_eval_and_fscore(dev):
+    """L2_ChamferEval_1000 / F1Score (completion_trainer/Latent_SDE_Trainer.py:41-53) against the float64 brute-force
+    NN distances of the oracle, including a pair with no point under the threshold (0/0 -> 0)."""
+    from ldt_b200 import metrics
+    g = torch.Generator().manual_seed(8)
+    a = torch.rand((5, 300, 3), generator=g) * 0.2
+    b = a[:, torch.randperm(300, generator=g)[:256]] + 0.01 * torch.randn((5, 256, 3), generator=g)
+    b[4] += 5.0                                                        # far away: precision 0 both ways
+    d1, _, d2, _ = O.nn_distance_f64(a, b)
+    want_cd = (d1.mean() + d2.mean()) * 1000
+    got_cd = metrics.L2_ChamferEval_1000(a.to(dev), b.to(dev))
+    assert abs(float(got_cd) - float(want_cd)) <= 1e-5 * float(want_cd)
+    f, p1, p2 = metrics.F1Score(a.to(dev), b.to(dev))
+    wp1, wp2 = (d1.float() < 0.001).float().mean(1), (d2.float() < 0.001).float().mean(1)
+    wf = 2 * wp1 * wp2 / (wp1 + wp2)
+    wf[torch.isnan(wf)] = 0
+    assert torch.allclose(p1.cpu(), wp1, atol=1 / 300 + 1e-6) and torch.allclose(p2.cpu(), wp2, atol=1 / 256 + 1e-6)
+    assert torch.allclose(f.cpu(), wf, atol=2e-2) and float(f[4]) == 0.0

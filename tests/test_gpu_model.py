@@ -355,3 +355,106 @@ def test_completion_sample_end_to_end(dev):
                                   condition=condition)
         pts = comp.sample((B, 2048), given_eps=eps)
     assert pts.shape == (B, 2048, 3) and torch.isfinite(pts).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# correctors, print_steps, PNDM
+# ------------------------------------------------------------------------------------------------
+def _stand_in_score_fn(sde):
+    def score_fn(t, x, label=None, condition=None):
+        params = 0.3 * x + torch.sin(5.0 * t)[:, None, None]
+        return -params / torch.sqrt(sde.var(t))[:, None, None], params
+    return score_fn
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("pc_ancestral", dict(predictor="ancestral", corrector="ancestral", corrector_steps=2)),
+    ("pc_langevin", dict(predictor="eulermaruyama", corrector="langevin", corrector_steps=1)),
+    ("c_only_ancestral", dict(predictor=None, corrector="ancestral", corrector_steps=1, denoise=False)),
+    ("print_steps", dict(predictor="ancestral", corrector=None, corrector_steps=1, print_steps=4)),
+])
+def test_generic_sampler_correctors_and_trajectory_match_reference_golden(dev, tag, kw):
+    from ldt_b200 import DiffusionVPSDE
+    g = golden("sde_ext.npz")
+    sde = DiffusionVPSDE(ns(airplane_config()).sde, device=dev)
+    it = iter(list(g[f"{tag}_noise"].to(dev)))
+    args = dict(score_fn=_stand_in_score_fn(sde), num_samples=32, N=5, shape=(32, 4), time_eps=1e-6,
+                probability_flow=False, denoise=True, snr=0.16, device=dev)
+    args.update(kw)
+    real = torch.randn_like
+    torch.randn_like = lambda x, *a, **k: next(it)
+    try:
+        torch.manual_seed(33)
+        out = sde.sample_discrete(**args)
+    finally:
+        torch.randn_like = real
+    out = torch.stack(out) if isinstance(out, list) else out
+    want = g[f"{tag}_out"]
+    assert out.shape == want.shape
+    if tag == "pc_langevin":
+        # the step size is a ratio of two global norms (reduction order differs from torch.norm's) and at snr 0.16 the
+        # iterates grow to ~3e2: compare against the tensor's scale, max|delta| / rms
+        assert rel_rms_err(out, want) < 1e-5, rel_rms_err(out, want)
+    else:
+        assert torch.allclose(out.cpu(), want, rtol=3e-5, atol=3e-6), (out.cpu() - want).abs().max()
+
+
+def test_pndm_matches_reference_golden(dev):
+    from ldt_b200 import DiffusionVPSDE
+    g = golden("sde_ext.npz")
+    c = ns(airplane_config()).sde
+    c.sample_N = 6
+    sde = DiffusionVPSDE(c, device=dev)
+    torch.manual_seed(33)
+    out = sde.sample_discrete(_stand_in_score_fn(sde), 32, 6, "pndm", None, 1, (32, 4), 1e-6, False, True, 0.16, dev)
+    assert torch.allclose(out.cpu(), g["pndm_out"], rtol=3e-5, atol=3e-6), (out.cpu() - g["pndm_out"]).abs().max()
+    # any batch size runs (the reference's broadcast restricts it to 1 and shape[0])
+    out5 = sde.sample_discrete(_stand_in_score_fn(sde), 5, 6, "pndm", None, 1, (32, 4), 1e-6, False, True, 0.16, dev)
+    assert out5.shape == (5, 32, 4) and torch.isfinite(out5).all()
+
+
+def test_fused_sampler_with_corrector_and_print_steps_equals_stepwise(dev):
+    """Ancestral predictor + AncestralCorrector (2 corrector steps) and the print_steps trajectory through the replayed
+    graph == the generic per-step path (same kernels, same Philox draws in the reference's draw order)."""
+    from ldt_b200 import DiffusionVPSDE
+    cfg = small_score_cfg()
+    model, _ = build_score(cfg, 11, dev)
+    sde = DiffusionVPSDE(ns(airplane_config()).sde, device=dev)
+    tr = _Trainer(model, sde)
+    N, B = 9, 4
+    outs = []
+    for fn in (tr.score_fn, lambda t, x, label=None, condition=None: tr.score_fn(t, x)):
+        torch.manual_seed(5); torch.cuda.manual_seed(5)
+        outs.append(sde.sample_discrete(fn, B, N, "ancestral", "ancestral", 2, (32, 120), 1e-6, False, True, 0.16, dev,
+                                        print_steps=6))
+        outs.append(torch.cuda.default_generators[0].get_offset())
+    fused, off_f, generic, off_g = outs
+    assert off_f == off_g
+    assert len(fused) == len(generic) == 1 + N // ((N - 1) // 4) + 1
+    for a, b in zip(fused, generic):
+        assert rel_rms_err(a, b) < 1e-5, rel_rms_err(a, b)
+
+
+def test_score_unet_vs_reference_golden_and_fused_loop(dev):
+    """``unet: True`` (score.py:67-83,138-146): forward vs the reference golden (both bars), then the replayed graph
+    against the stepwise public API."""
+    from ldt_b200 import DiffusionVPSDE
+    from tests.helpers import small_unet_score_cfg
+    cfg = small_unet_score_cfg()
+    g = golden("score_unet.npz")
+    model, sd = build_score(cfg, 19, dev)
+    with torch.no_grad():
+        out = model(g["x"].to(dev), g["t"].to(dev))
+        out_c = model(g["x"].to(dev), g["t"].to(dev), condition=(None, g["img_cond"].to(dev)))
+    check_vs_fp32(out, g["params"])
+    check_vs_fp32(out_c, g["params_cond"])
+    emu = emulated(lambda: O.score_forward_unet(sd, cfg, g["x"], g["t"]))
+    assert rms_rel_err(out, emu) < TOL_RMS_EMUL, rms_rel_err(out, emu)
+    sde = DiffusionVPSDE(ns(airplane_config()).sde, device=dev)
+    tr = _Trainer(model, sde)
+    torch.manual_seed(3); torch.cuda.manual_seed(3)
+    fused = sde.sample_discrete(tr.score_fn, 4, 8, "ancestral", None, 1, (32, 120), 1e-6, False, True, 0.01, dev)
+    torch.manual_seed(3); torch.cuda.manual_seed(3)
+    generic = sde.sample_discrete(lambda t, x, label=None, condition=None: tr.score_fn(t, x), 4, 8, "ancestral", None, 1,
+                                  (32, 120), 1e-6, False, True, 0.01, dev)
+    assert rel_rms_err(fused, generic) < 1e-5, rel_rms_err(fused, generic)
