@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--sde-steps", type=int, default=1000, help="reverse-SDE steps (config: 1000)")
     ap.add_argument("--points", type=int, default=2048)
     ap.add_argument("--cd-clouds", type=int, default=192, help="clouds per set for the Chamfer-matrix metric")
+    ap.add_argument("--emd-clouds", type=int, default=24, help="clouds per set for the approximate-EMD metric")
+    ap.add_argument("--completion-batch", type=int, default=64, help="clouds per GPU of the completion workload")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the EMD / completion secondary metrics")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-steps", type=int, default=3)
     return ap.parse_args()
@@ -334,6 +337,59 @@ def main():
                            "peak": 148 * 128 * 2 * 1.965e9 / 1e12, "peak_source": "nominal: 148 SMs x 128 FP32 lanes x 2 x 1.965 GHz",
                            "frac": pair_evals * 8 / t_cd / (148 * 128 * 2 * 1.965e9)}}
 
+    # ---- secondary: approximate-EMD cloud-pairs/s and the completion workload (BASELINE configs[4]) ----
+    emd = completion = None
+    if rank == 0 and not args.no_secondary:
+        n = args.emd_clouds
+        g = torch.Generator().manual_seed(7)
+        a = torch.rand((n, P, 3), generator=g).to(dev)
+        b = torch.rand((n, P, 3), generator=g).to(dev)
+        ops.pairwise_emd(a, b)
+        torch.cuda.synchronize()
+        ev0.record()
+        ops.pairwise_emd(a, b)
+        ev1.record()
+        torch.cuda.synchronize()
+        t_emd = ev0.elapsed_time(ev1) / 1e3
+        emd = {"metric": "approximate-EMD cloud-pairs/sec @2048x2048 pts (ApproxMatch + MatchCost forward)",
+               "value": n * n / t_emd, "unit": "pairs/s", "matrix": f"{n}x{n}"}
+        # completion: per-sample conditioning (image vector + 32 condition tokens), cross-attention in even blocks;
+        # the ConditionNet prologue (FPS + k-NN kernels, torch layers) is inside the timed region, as in
+        # completion_trainer/Latent_SDE_Trainer.py:147-170.  512 clouds over 8 GPUs = 64 per GPU.
+        cc = ns(airplane_config())
+        cc.score.condition = True
+        torch.manual_seed(0)
+        cmodel = Score(cc.score).to(dev).eval()
+        ctr = Trainer()
+        ctr.model = cmodel
+        Bc = args.completion_batch
+        g = torch.Generator().manual_seed(99)
+        views = torch.rand((Bc, 3, 224, 224), generator=g).to(dev)
+        part = torch.randn((Bc, 2048, 3), generator=g)
+        part = (part / part.norm(dim=-1).max(dim=1)[0][:, None, None]).to(dev)
+
+        def completion_step():
+            with torch.no_grad():
+                condition = cmodel.c_net({"img": views, "pts": part})
+                eps = sde.sample_discrete(score_fn=ctr.score_fn, N=N, corrector=None, predictor=c.sde.predictor, corrector_steps=1,
+                                          shape=(c.score.z_scale, c.score.z_dim), time_eps=c.sde.sample_time_eps, label=None,
+                                          denoise=c.sde.denoise, device=dev, num_samples=Bc, probability_flow=False,
+                                          snr=c.sde.snr, condition=condition)
+                return comp.sample((Bc, P), given_eps=eps)
+
+        completion_step()
+        torch.cuda.synchronize()
+        ev0.record()
+        completion_step()
+        ev1.record()
+        torch.cuda.synchronize()
+        t_c = ev0.elapsed_time(ev1) / 1e3
+        # 18.14 GFLOP per sample-step (+ per-sample adaLN, - K/V of the step-invariant condition tokens)
+        completion = {"metric": "completion clouds/sec (ConditionNet + conditional SDE sample + decode @2048 pts)",
+                      "value": Bc / t_c, "unit": "clouds/s", "batch_per_gpu": Bc, "sde_steps": N,
+                      "tensor_tflops": Bc * N * 18.14e9 / t_c / 1e12}
+        del cmodel
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -355,7 +411,8 @@ def main():
                        "l2": "per-step working set (604 MB bf16 weights + activations) exceeds the 126 MB L2; no flush needed"},
             "e2e": {"value": clouds / t_e2e, "unit": "clouds/s", "h2d_bytes_per_step": B * 32 * 120 * 4,
                     "d2h_bytes_per_step": B * P * 3 * 4, "api": "DiffusionVPSDE.sample_discrete(score_fn=Trainer.score_fn) + Compressor.sample"},
-            "gpu_launches": gpu_launches, "roofline": roof, "cpu_baseline": cpu, "cd": cd, "clocks": clocks,
+            "gpu_launches": gpu_launches, "roofline": roof, "cpu_baseline": cpu, "cd": cd, "emd": emd,
+            "completion": completion, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
