@@ -156,6 +156,13 @@ int ldt_time_embedding(int R, int half, int D, const float* t, const float* freq
 int ldt_attention_nk32(int B, int H, int Nq, int dh, const void* q, int ldq, const void* k, const void* v,
                        int ldkv, void* o, void* stream);
 
+/* The transposed shape: a SHORT query set over a LONG key set (Nq = 32 latent tokens attending to the Nk = 2048 decoded
+ * points in DecoderBlock.compute_posterior, model/Compressor/Network.py:62-77), online softmax over key chunks.
+ * Same operand and output layouts as ldt_attention_nk32 (q [B*Nq, ldq], k/v [B*Nk, ldkv], o = [B,H,Nq,dh] contiguous).
+ * dh must be 32. */
+int ldt_attention_longkv(int B, int H, int Nq, int Nk, int dh, const void* q, int ldq, const void* k, const void* v,
+                         int ldkv, void* o, void* stream);
+
 /* Fused Q/K/V projection + self-attention of one score-net block (fc_q, fc_kv and compute_attention of
  * model/layers.py:186-197 in one kernel; Q, K, V stay on chip).
  *   A   bf16 [B*32, lda]   LayerNorm'd + modulated activations (K = hidden columns used)

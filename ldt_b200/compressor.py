@@ -8,13 +8,20 @@ load with ``strict=True`` (trainer/Latent_SDE_Trainer.py:269-273).  Only the dec
 sm_100a kernels: per layer  Conv1d(z_dim->hidden) on the 32 latent tokens, K/V projection, LayerNorm(affine),
 Q projection of the 2048 query rows, 2048x32 cross-attention, output projection + residual, LayerNorm, MLP with
 GELU epilogue + residual (DecoderBlock.forward :80-83 -> ResidualBlock.forward c=None branch,
-model/layers.py:224-226); finally Conv1d(hidden->3).  The encoder (bottom_up/top_down/forward) is training /
-reconstruction only and is out of scope: ``forward`` raises.
+model/layers.py:224-226); finally Conv1d(hidden->3).
+
+``forward(x)`` (bottom_up + top_down, Network.py:188-249: the inference path of the set-VAE encoder)
+runs on the same kernels: FPS + k-NN grouping (``ldt_furthest_point_sample`` / ``ldt_knn_indices``), the AdaLN encoder
+blocks on the 32 group tokens, the posterior blocks whose 32 tokens attend to the 2048 decoded points
+(``ldt_attention_longkv``), and the decoder blocks above.  The small point-wise layers around the grouping (input
+Conv1d(3->hidden), the grouper's Conv+BatchNorm stack, MiniPointnet, ActNorm) are evaluated with torch functional ops
+straight from the parameters.  Inference only: the KL terms are returned, nothing is differentiable.
 """
 from __future__ import annotations
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import ops
 from ._lib import EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_GATE_RESID_F32
@@ -189,14 +196,20 @@ class Compressor(nn.Module):
             self.conv_in.initialized += 1.0
 
     def forward(self, x, num_points=None, label=None):
-        raise NotImplementedError(
-            "ldt_b200.Compressor implements the sampling decoder only; the encoder (bottom_up/top_down) is "
-            "training/reconstruction code outside the B200 hot path (SURVEY.md section 2, row 4)")
+        """Bidirectional inference (Network.py:235-249): x [B, N, 3] -> dict(set, posteriors, kls, all_eps, all_logqz, max)."""
+        if label is not None and self.class_condition:
+            raise NotImplementedError("ldt_b200.Compressor: class-conditional encoding is not supported")
+        with torch.no_grad():
+            bup = self.bottom_up(x)
+            tdn = self.top_down(bup["outputs"], num_points=num_points)
+            all_eps = torch.cat(tdn["all_eps"], dim=1).transpose(1, 2)
+            return {"set": self.postprocess(tdn["set"]), "posteriors": tdn["posteriors"], "kls": tdn["kls"],
+                    "all_eps": all_eps, "all_logqz": tdn["all_logqz"], "max": bup["max"]}
 
     # ------------------------------------------------------------------------------------------
     def _fingerprint(self):
         return tuple((p.data_ptr(), p._version) for n, p in self.named_parameters()
-                     if n.startswith(("decoder.", "output.", "init_set.")))
+                     if n.startswith(("decoder.", "output.", "init_set.", "encoder.")))
 
     def packed(self):
         key = self._fingerprint()
@@ -206,12 +219,45 @@ class Compressor(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("ldt_b200.Compressor runs on CUDA only (no CPU fallback); call .to('cuda') first")
         H = self.hidden_dim
-        P = {"layers": []}
+        P = {"layers": [], "post": [], "enc": []}
         with torch.no_grad():
+            f32 = lambda t: t.detach().float().contiguous()
+
+            def mlp_w(a):
+                return {"w_fc1": ops.pack_weight(a.mlp.fc._modules["0"]._modules["0"].weight),
+                        "b_fc1": f32(a.mlp.fc._modules["0"]._modules["0"].bias),
+                        "w_fc2": ops.pack_weight(a.mlp.out.weight), "b_fc2": f32(a.mlp.out.bias)}
+
+            def attn_w(a):
+                return {"w_q": ops.pack_weight(a.fc_q.weight), "b_q": f32(a.fc_q.bias),
+                        "w_kv": ops.pack_weight(a.fc_kv.weight), "b_kv": f32(a.fc_kv.bias),
+                        "w_o": ops.pack_weight(a.fc_o.weight), "b_o": f32(a.fc_o.bias)}
+
+            # encoder (Network.py:32-45): per layer `encoder_layers` AdaLN blocks + a FinalLayer; every adaLN consumes the
+            # same SiLU(pos), so all of them are one GEMM against the row-concatenated weights
+            ada_w, ada_b = [], []
+            for l in range(self.n_layers):
+                e = self.encoder._modules[str(l)]
+                blocks = []
+                for j in range(self.cfg.encoder_layers):
+                    a = e.atts._modules[str(j)]
+                    blocks.append({**attn_w(a), **mlp_w(a)})
+                    ada_w.append(a.adaLN._modules["1"].weight.detach())
+                    ada_b.append(a.adaLN._modules["1"].bias.detach())
+                ada_w.append(e.conv_out.adaLN._modules["1"].weight.detach())
+                ada_b.append(e.conv_out.adaLN._modules["1"].bias.detach())
+                P["enc"].append({"blocks": blocks, "w_out": ops.pack_weight(e.conv_out.ln.weight), "b_out": f32(e.conv_out.ln.bias)})
+            P["w_ada"] = ops.pack_weight(torch.cat(ada_w, dim=0))
+            P["b_ada"] = torch.cat(ada_b).float().contiguous()
             for l in range(self.n_layers):
                 d = self.decoder._modules[str(l)]
+                a = d.att
+                # posterior block `att` (c = None: affine LayerNorms) and the SiLU -> Conv1d prior head (:55,62-77)
+                P["post"].append({**attn_w(a), **mlp_w(a),
+                                  "n1w": f32(a.norm1.norm.weight), "n1b": f32(a.norm1.norm.bias),
+                                  "n2w": f32(a.norm2.norm.weight), "n2b": f32(a.norm2.norm.bias),
+                                  "w_prior": ops.pack_weight(d.prior._modules["1"].weight), "b_prior": f32(d.prior._modules["1"].bias)})
                 a = d.att1
-                f32 = lambda t: t.detach().float().contiguous()
                 P["layers"].append({
                     "w_ln": ops.pack_weight(d.ln.weight), "b_ln": f32(d.ln.bias),
                     "w_q": ops.pack_weight(a.fc_q.weight), "b_q": f32(a.fc_q.bias),
@@ -268,24 +314,195 @@ class Compressor(nn.Module):
             q = torch.empty((MQ, H), dtype=bf, device=dev)
             att = torch.empty((MQ, H), dtype=bf, device=dev)
             hid = torch.empty((MQ, int(self.mlp_ratio * H)), dtype=bf, device=dev)
+            bufs = (e_a, xx, kv, a, q, att, hid)
             for idx in range(self.n_layers):
                 W = P["layers"][self.n_layers - 1 - idx]  # reversed(self.decoder), :263
                 chunk = eps[:, idx * Z:(idx + 1) * Z]     # torch.split(...)[idx], :262
-                _cast_strided(chunk, eps.stride(0), Z, e_a)
-                ops.gemm(e_a, W["w_ln"], W["b_ln"], xx, EPI_BIAS_BF16)              # x = self.ln(eps)        :81
-                ops.gemm(xx, W["w_kv"], W["b_kv"], kv, EPI_BIAS_BF16)               # kv = fc_kv(x)   layers.py:187
-                ops.layernorm_mod(o, a, weight=W["n1w"], bias=W["n1b"])             # norm1 (affine)          :225
-                ops.gemm(a, W["w_q"], W["b_q"], q, EPI_BIAS_BF16)                   # q = fc_q(norm1(o))
-                ops.attention_nk32(B, heads, num_points, dh, q, H, kv, _PtrView(kv.data_ptr() + 2 * H), 2 * H, att)
-                ops.gemm(att, W["w_o"], W["b_o"], o, EPI_GATE_RESID_F32, resid=o)   # o = o + fc_o(att)
-                ops.layernorm_mod(o, a, weight=W["n2w"], bias=W["n2b"])             # norm2                   :226
-                ops.gemm(a, W["w_fc1"], W["b_fc1"], hid, EPI_BIAS_GELU_BF16)
-                ops.gemm(hid, W["w_fc2"], W["b_fc2"], o, EPI_GATE_RESID_F32, resid=o)
+                self._decoder_block(W, B, num_points, chunk, eps.stride(0), o, bufs)
             ob = ops.cast_pad_bf16(o, H, out=a)
             pts8 = torch.empty((MQ, 8), dtype=torch.float32, device=dev)
             ops.gemm(ob, P["w_out"], P["b_out"], pts8, EPI_BIAS_F32)               # self.output(o)           :266
             out = pts8[:, :3].reshape(B, num_points, 3).contiguous()
         return self.postprocess(out)
+
+    def _decoder_block(self, W, B, num_points, chunk, ld_chunk, o, bufs):
+        """DecoderBlock.forward (:80-83): o [B*N, H] f32 (in place) attends to the layer's latent chunk [B*32, z_dim]."""
+        H, Z, heads = self.hidden_dim, self.z_dim, self.num_heads
+        e_a, xx, kv, a, q, att, hid = bufs
+        _cast_strided(chunk, ld_chunk, Z, e_a)
+        ops.gemm(e_a, W["w_ln"], W["b_ln"], xx, EPI_BIAS_BF16)              # x = self.ln(eps)        :81
+        ops.gemm(xx, W["w_kv"], W["b_kv"], kv, EPI_BIAS_BF16)               # kv = fc_kv(x)   layers.py:187
+        ops.layernorm_mod(o, a, weight=W["n1w"], bias=W["n1b"])             # norm1 (affine)          :225
+        ops.gemm(a, W["w_q"], W["b_q"], q, EPI_BIAS_BF16)                   # q = fc_q(norm1(o))
+        ops.attention_nk32(B, heads, num_points, H // heads, q, H, kv, _PtrView(kv.data_ptr() + 2 * H), 2 * H, att)
+        ops.gemm(att, W["w_o"], W["b_o"], o, EPI_GATE_RESID_F32, resid=o)   # o = o + fc_o(att)
+        ops.layernorm_mod(o, a, weight=W["n2w"], bias=W["n2b"])             # norm2                   :226
+        ops.gemm(a, W["w_fc1"], W["b_fc1"], hid, EPI_BIAS_GELU_BF16)
+        ops.gemm(hid, W["w_fc2"], W["b_fc2"], o, EPI_GATE_RESID_F32, resid=o)
+
+    # ------------------------------------------------------------------------------------------
+    # encoder inference path (SURVEY.md 8f4)
+    # ------------------------------------------------------------------------------------------
+    def _bn(self, m, x):
+        return F.batch_norm(x, m.running_mean, m.running_var, m.weight, m.bias, training=False, eps=1e-5)
+
+    def _group(self, g, normalize, xyz, feature, groups, k):
+        """LocalGrouper.forward (Compressor/layers.py:288-319) from the parameters of sub-tree ``g``; FPS and k-NN on the
+        sm_100a kernels.  xyz [B,3,N], feature [B,D,N] -> (centres [B,3,S], group features [B,D,S])."""
+        from .condition import cluster, gather_points
+        pts, fea = xyz.transpose(1, 2), feature.transpose(1, 2)
+        B = pts.shape[0]
+        new_xyz, fps_idx, idx = cluster(pts, groups, k)
+        anchor = gather_points(fea, fps_idx)
+        grouped = torch.cat([gather_points(fea, idx), gather_points(pts, idx)], dim=-1)
+        normalize = normalize.lower() if isinstance(normalize, str) else None
+        if normalize in ("center", "anchor"):
+            mean = grouped.mean(dim=2, keepdim=True) if normalize == "center" else torch.cat([anchor, new_xyz], dim=-1).unsqueeze(-2)
+            centred = grouped - mean
+            std = torch.std(centred.reshape(B, -1), dim=-1, keepdim=True)[:, :, None, None]
+            grouped = g.affine_alpha * (centred / (std + 1e-5)) + g.affine_beta
+        x = torch.cat([grouped, anchor.unsqueeze(2).expand(-1, -1, k, -1)], dim=-1)
+        b, s_, kk, d = x.shape
+        x = x.permute(0, 1, 3, 2).reshape(b * s_, d, kk)
+        ex = g.extraction
+        t = ex.transfer.net
+        x = F.relu(self._bn(t._modules["1"], F.conv1d(x, t._modules["0"].weight, t._modules["0"].bias)))
+        op = ex.operation._modules["0"]
+        y = F.relu(self._bn(op.net1._modules["1"], F.conv1d(x, op.net1._modules["0"].weight, op.net1._modules["0"].bias)))
+        x = F.relu(F.conv1d(y, op.net2._modules["0"].weight, op.net2._modules["0"].bias) + x)
+        return new_xyz.transpose(1, 2), x.amax(dim=-1).reshape(b, s_, -1).permute(0, 2, 1)
+
+    def _attn_block(self, W, B, x, kv_src, kv_tokens, n1, n2, gate1, gate2, bufs, mod_stride=0):
+        """One ResidualBlock on the 32 group tokens with K/V taken from ``kv_src`` (bf16 [B*kv_tokens, H], NOT normalised:
+        compute_attention receives the raw ``y``, layers.py:184-187).  n1 / n2 are the keyword arguments of the two
+        LayerNorm passes (AdaLN shift/scale or affine weight/bias), gate1 / gate2 the AdaLN gates or None."""
+        H, T, heads = self.hidden_dim, self.z_scales, self.num_heads
+        a, q, kv, att, hid = bufs
+        ops.layernorm_mod(x, a, **n1)
+        ops.gemm(a, W["w_q"], W["b_q"], q, EPI_BIAS_BF16)
+        ops.gemm(kv_src, W["w_kv"], W["b_kv"], kv, EPI_BIAS_BF16)
+        vptr = _PtrView(kv.data_ptr() + 2 * H)
+        if kv_tokens == 32:
+            ops.attention_nk32(B, heads, T, H // heads, q, H, kv, vptr, 2 * H, att)
+        else:
+            ops.attention_longkv(B, heads, T, kv_tokens, H // heads, q, H, kv, vptr, 2 * H, att)
+        ops.gemm(att, W["w_o"], W["b_o"], x, EPI_GATE_RESID_F32, resid=x, gate=gate1, gate_stride=mod_stride, rows_per_gate=T)
+        ops.layernorm_mod(x, a, **n2)
+        ops.gemm(a, W["w_fc1"], W["b_fc1"], hid, EPI_BIAS_GELU_BF16)
+        ops.gemm(hid, W["w_fc2"], W["b_fc2"], x, EPI_GATE_RESID_F32, resid=x, gate=gate2, gate_stride=mod_stride, rows_per_gate=T)
+
+    def bottom_up(self, pts, label=None):
+        """Network.py:188-209: points [B,N,3] -> per-layer encoder outputs (token-major f32 [B*32, H]) and max feature."""
+        cfg = self.cfg
+        dev = self.output.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("ldt_b200.Compressor runs on CUDA only (no CPU fallback); call .to('cuda') first")
+        if cfg.pos_embedding == "mlp":
+            raise NotImplementedError("ldt_b200.Compressor: pos_embedding 'mlp' (per-token conditioning) is not supported")
+        if cfg.encoder_dropout_p != 0:
+            raise NotImplementedError("ldt_b200.Compressor is an inference path: encoder_dropout_p must be 0")
+        P = self.packed()
+        H, T, Pd = self.hidden_dim, self.z_scales, self.p_dim
+        pts = pts.to(dev).float()
+        if cfg.norm_input:
+            pts = (pts - pts.mean(dim=1, keepdim=True)) / pts.std(dim=1, keepdim=True)
+        B = pts.shape[0]
+        pts = pts.transpose(1, 2)
+        x = F.conv1d(pts, self.input.weight, self.input.bias)
+        if cfg.pre_group:
+            pts, x = self._group(self.pre_grouper, cfg.cluster_norm, pts, x, 256, 32)
+        center, x = self._group(self.group, cfg.cluster_norm, pts, x, T, pts.shape[2] // T * 2)
+        pe = self.pos_embedding                                           # MiniPointnet, Network.py:86-101
+        y = F.relu(self._bn(pe.bn1, F.conv1d(center, pe.conv1.weight, pe.conv1.bias)))
+        y = F.relu(self._bn(pe.bn2, F.conv1d(y, pe.conv2.weight, pe.conv2.bias)))
+        pos = F.linear(y.amax(dim=2), pe.fc.weight, pe.fc.bias).contiguous()    # [B, p_dim]
+        x = x.transpose(1, 2)                                              # [B, 32, H]
+        if self.ActNorm is not None:
+            x = (x - self.conv_in.shift) * torch.exp(-self.conv_in.log_scale)   # ActNorm.forward, model/layers.py:103-107
+        x = x.reshape(B * T, H).contiguous()                               # token-major residual stream
+        # all adaLN rows of the encoder from SiLU(pos) in one GEMM
+        sc = torch.empty((B, Pd), dtype=torch.bfloat16, device=dev)
+        ops.cond_silu(torch.zeros((1, Pd), device=dev), None, pos, None, sc)
+        L = cfg.encoder_layers
+        row = (6 * L + 2) * H
+        mod = torch.empty((B, self.n_layers * row), dtype=torch.float32, device=dev)
+        ops.gemm(sc, P["w_ada"], P["b_ada"], mod, EPI_BIAS_F32)
+        stride = mod.shape[1]
+        mv = lambda off: _PtrView(mod.data_ptr() + 4 * off)
+        bf = torch.bfloat16
+        bufs = tuple(torch.empty((B * T, w), dtype=bf, device=dev) for w in (H, H, 2 * H, H, int(self.mlp_ratio * H)))
+        xb = torch.empty((B * T, H), dtype=bf, device=dev)
+        outputs = []
+        for l in range(self.n_layers):
+            for j, W in enumerate(P["enc"][l]["blocks"]):
+                base = l * row + j * 6 * H
+                ops.cast_pad_bf16(x, H, out=xb)                            # layer(x, x, pos): K/V from the raw x
+                self._attn_block(W, B, x, xb, 32,
+                                 dict(shift=mv(base), scale=mv(base + H), mod_stride=stride, rows_per_mod=T),
+                                 dict(shift=mv(base + 3 * H), scale=mv(base + 4 * H), mod_stride=stride, rows_per_mod=T),
+                                 mv(base + 2 * H), mv(base + 5 * H), bufs, mod_stride=stride)
+            base = l * row + L * 6 * H                                     # FinalLayer: (shift, scale) then Conv1d
+            ops.layernorm_mod(x, bufs[0], shift=mv(base), scale=mv(base + H), mod_stride=stride, rows_per_mod=T)
+            o = torch.empty((B * T, H), dtype=torch.float32, device=dev)
+            ops.gemm(bufs[0], P["enc"][l]["w_out"], P["enc"][l]["b_out"], o, EPI_BIAS_F32)
+            outputs.append(o)
+        return {"outputs": outputs, "max": x.max()}
+
+    def top_down(self, encoder_out, num_points=None, label=None):
+        """Stochastic top-down pass (Network.py:211-233).  Tensors in the returned dict use the reference's
+        channels-first shapes ([B, z_dim, 32] latents, [B, N, 3] set)."""
+        P = self.packed()
+        dev = self.output.weight.device
+        H, T, Z, heads = self.hidden_dim, self.z_scales, self.z_dim, self.num_heads
+        B = encoder_out[0].shape[0] // T
+        N = num_points if num_points is not None else self.outsize
+        bf = torch.bfloat16
+        o = self.initial_set(B, N)
+        MQ, MT = B * N, B * T
+        dbufs = (torch.zeros((MT, _pad_to(Z, 64)), dtype=bf, device=dev), torch.empty((MT, H), dtype=bf, device=dev),
+                 torch.empty((MT, 2 * H), dtype=bf, device=dev), torch.empty((MQ, H), dtype=bf, device=dev),
+                 torch.empty((MQ, H), dtype=bf, device=dev), torch.empty((MQ, H), dtype=bf, device=dev),
+                 torch.empty((MQ, int(self.mlp_ratio * H)), dtype=bf, device=dev))
+        pbufs = (torch.empty((MT, H), dtype=bf, device=dev), torch.empty((MT, H), dtype=bf, device=dev),
+                 torch.empty((MQ, 2 * H), dtype=bf, device=dev), torch.empty((MT, H), dtype=bf, device=dev),
+                 torch.empty((MT, int(self.mlp_ratio * H)), dtype=bf, device=dev))
+        ob = torch.empty((MQ, H), dtype=bf, device=dev)
+        xb = torch.empty((MT, H), dtype=bf, device=dev)
+        zero_row = torch.zeros((1, H), device=dev)
+        cf = lambda t, c: t.view(B, T, c).transpose(1, 2)                    # token-major -> [B, C, 32]
+        posteriors = [(o.view(B, N, H).transpose(1, 2).clone(), None, None)]
+        kls, all_eps, all_logqz = [], [], []
+        for idx in range(self.n_layers):
+            Li = self.n_layers - 1 - idx                                     # reversed(self.decoder)
+            W = P["post"][Li]
+            x = encoder_out[Li].clone()
+            n1, n2 = dict(weight=W["n1w"], bias=W["n1b"]), dict(weight=W["n2w"], bias=W["n2b"])
+            if idx != 0:                                                     # att(x, o, c): tokens attend to the current set
+                ops.cast_pad_bf16(o, H, out=ob)
+                self._attn_block(W, B, x, ob, N, n1, n2, None, None, pbufs)
+            else:
+                ops.cast_pad_bf16(x, H, out=xb)
+                self._attn_block(W, B, x, xb, 32, n1, n2, None, None, pbufs)
+            sx = pbufs[0]
+            ops.cond_silu(zero_row, None, x, None, sx)                        # prior = Conv1d(SiLU(x))  :55
+            post = torch.empty((MT, 2 * Z), dtype=torch.float32, device=dev)
+            ops.gemm(sx, W["w_prior"], W["b_prior"], post, EPI_BIAS_F32)
+            mu = cf(post[:, :Z], Z)
+            logvar = cf(post[:, Z:], Z).clamp(self.cfg.min_sigma, 10.0)
+            noise = torch.randn(mu.shape).to(mu)                             # sample(), Network.py:26-29 (CPU generator)
+            eps = mu + torch.exp(logvar / 2.0) * noise
+            logqz = -0.5 * torch.square(eps - mu) / torch.exp(logvar) - 0.5 * logvar - 0.9189385332
+            logpz = -0.5 * torch.square(eps) - 0.9189385332
+            eps_tok = eps.transpose(1, 2).reshape(MT, Z).contiguous()
+            self._decoder_block(P["layers"][Li], B, N, eps_tok, Z, o, dbufs)
+            all_eps.append(eps)
+            posteriors.append((eps, mu, logvar))
+            kls.append(logqz - logpz)
+            all_logqz.append(logqz)
+        pts8 = torch.empty((MQ, 8), dtype=torch.float32, device=dev)
+        ops.gemm(ops.cast_pad_bf16(o, H, out=ob), P["w_out"], P["b_out"], pts8, EPI_BIAS_F32)
+        return {"set": pts8[:, :3].reshape(B, N, 3).contiguous(), "posteriors": posteriors, "kls": kls,
+                "all_logqz": all_logqz, "all_eps": all_eps}
 
     @staticmethod
     def postprocess(x):

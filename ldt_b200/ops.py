@@ -220,6 +220,12 @@ def attention_nk32(B: int, H: int, Nq: int, dh: int, q, ldq: int, k, v, ldkv: in
               "ldt_attention_nk32")
 
 
+def attention_longkv(B: int, H: int, Nq: int, Nk: int, dh: int, q, ldq: int, k, v, ldkv: int, o) -> None:
+    with torch.cuda.device(o.device), _launch("attention_longkv"):
+        check(load().ldt_attention_longkv(B, H, Nq, Nk, dh, ptr(q), ldq, ptr(k), ptr(v), ldkv, ptr(o), stream_ptr()),
+              "ldt_attention_longkv")
+
+
 def qkv_attention(B: int, H: int, A, Wp, bias_p, out) -> None:
     """Fused head-major QKV projection + 32-token self-attention (ldt_qkv_attention_bf16)."""
     K = A.shape[1]

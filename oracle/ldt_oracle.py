@@ -431,10 +431,11 @@ def compute_cd_metrics(sample_pcs, ref_pcs, nn_fn):
 # --------------------------------------------------------------------------------------------------
 # deterministic synthetic weights shared by the golden generator and the tests
 # --------------------------------------------------------------------------------------------------
-def synth_state_dict(shapes: dict, seed: int) -> dict:
+def synth_state_dict(shapes: dict, seed: int, gain: float = 1.5) -> dict:
     """Fill {name: shape} with seeded values in sorted-key order (independent of module registration order).
 
-    Conv/Linear weights ~ N(0, 1/fan_in) * 1.5, biases ~ N(0, 0.1), norm weights ~ 1 + N(0, 0.1), the decoder
+    Conv/Linear weights ~ N(0, 1/fan_in) * gain (1.5 by default; the deep stochastic encoder test uses a smaller gain so
+    that the map stays well conditioned), biases ~ N(0, 0.1), norm weights ~ 1 + N(0, 0.1), the decoder
     prior ~ U(0,1) like its initialiser (Compressor/layers.py:24).  Same torch build => same bits everywhere.
     """
     g = torch.Generator().manual_seed(seed)
@@ -453,7 +454,7 @@ def synth_state_dict(shapes: dict, seed: int) -> dict:
             out[name] = 1.0 + 0.1 * torch.randn(shape, generator=g)
         elif name.endswith("weight") and len(shape) >= 2:
             fan_in = int(np.prod(shape[1:]))
-            out[name] = torch.randn(shape, generator=g) * (1.5 / math.sqrt(fan_in))
+            out[name] = torch.randn(shape, generator=g) * (gain / math.sqrt(fan_in))
         else:
             out[name] = 0.1 * torch.randn(shape, generator=g)
     return out
@@ -540,3 +541,61 @@ def condition_net(sd, prefix, img, pts, patch_size, fps_fn):
     _, f = local_grouper(sd, prefix + "group.", p, f, patch_size, f.shape[1] // patch_size * 2, "center", fps_fn)
     pts_cond = F.conv1d(f, sd[prefix + "pc_conv_out.weight"], sd[prefix + "pc_conv_out.bias"])
     return pts_cond, img_cond
+
+
+# --------------------------------------------------------------------------------------------------
+# Compressor bidirectional inference: bottom_up + top_down (model/Compressor/Network.py:188-249)
+# --------------------------------------------------------------------------------------------------
+def mini_pointnet(sd, prefix, x):
+    """MiniPointnet.forward in eval mode (Network.py:86-101): [B,3,S] -> [B, p_dim]."""
+    x = F.relu(_bn_eval(sd, prefix + "bn1.", F.conv1d(x, sd[prefix + "conv1.weight"], sd[prefix + "conv1.bias"])))
+    x = F.relu(_bn_eval(sd, prefix + "bn2.", F.conv1d(x, sd[prefix + "conv2.weight"], sd[prefix + "conv2.bias"])))
+    return F.linear(x.max(dim=2)[0], sd[prefix + "fc.weight"], sd[prefix + "fc.bias"])
+
+
+def compressor_forward(sd, cfg, pts, fps_fn, num_points=None):
+    """Compressor.forward (eval mode, no label): pts [B,N,3] -> dict like the reference's.  Consumes the CPU generator
+    in the reference's order: B randperms (InitialSet), then one randn(mu.shape) per decoder layer (sample(), :26-29)."""
+    H = cfg.hidden_dim
+    x = pts.transpose(1, 2)
+    f = F.conv1d(x, sd["input.weight"], sd["input.bias"])
+    center, g = local_grouper(sd, "group.", x, f, cfg.z_scales, x.shape[2] // cfg.z_scales * 2, cfg.cluster_norm.lower(), fps_fn)
+    pos = mini_pointnet(sd, "pos_embedding.", center)
+    if cfg.ActNorm is not None:  # ActNorm.forward, model/layers.py:103-107
+        g = ((g.transpose(1, 2) - sd["conv_in.shift"]) * torch.exp(-sd["conv_in.log_scale"])).transpose(1, 2)
+    outputs = []
+    for i in range(cfg.n_layers):  # Encoder.forward, Network.py:41-45: layer(x, x, pos) -> K/V from the raw x
+        for j in range(cfg.encoder_layers):
+            g = residual_block_adaln(sd, f"encoder.{i}.atts.{j}.", g, g, pos, cfg.num_heads)
+        p = f"encoder.{i}.conv_out."
+        mod = F.linear(_q(F.silu(pos[:, None, :])), _q(sd[p + "adaLN.1.weight"]), sd[p + "adaLN.1.bias"]).transpose(1, 2)
+        shift, scale = mod.chunk(2, dim=1)
+        outputs.append(conv1x1(layer_norm_cf(g) * (1 + scale) + shift, sd[p + "ln.weight"], sd[p + "ln.bias"]))
+    # top_down, :211-233
+    B = pts.shape[0]
+    N = cfg.outsize if num_points is None else num_points
+    prior = sd["init_set.prior"]
+    mask = sample_mask(B, N, cfg.max_outputs)
+    o = prior[None].expand(B, -1, -1)[~mask, :].view(B, N, H).transpose(1, 2)
+    res = {"posteriors": [(o, None, None)], "kls": [], "all_eps": [], "all_logqz": []}
+    for idx in range(cfg.n_layers):
+        l = cfg.n_layers - 1 - idx
+        p = f"decoder.{l}."
+        xe = outputs[l]
+        h = residual_block_plain(sd, p + "att.", xe, o if idx != 0 else xe, cfg.num_heads)   # compute_posterior :62-77
+        post = conv1x1(F.silu(h), sd[p + "prior.1.weight"], sd[p + "prior.1.bias"])
+        mu = post[:, :post.shape[1] // 2, :]
+        logvar = post[:, post.shape[1] // 2:, :].clamp(cfg.min_sigma, 10.0)
+        eps = mu + torch.exp(logvar / 2.0) * torch.randn(mu.shape).to(mu)
+        logqz = -0.5 * torch.square(eps - mu) / torch.exp(logvar) - 0.5 * logvar - 0.9189385332
+        logpz = -0.5 * torch.square(eps) - 0.9189385332
+        xx = conv1x1(eps, sd[p + "ln.weight"], sd[p + "ln.bias"])
+        o = residual_block_plain(sd, p + "att1.", o, xx, cfg.num_heads)
+        res["all_eps"].append(eps)
+        res["posteriors"].append((eps, mu, logvar))
+        res["kls"].append(logqz - logpz)
+        res["all_logqz"].append(logqz)
+    res["set"] = conv1x1(o, sd["output.weight"], sd["output.bias"]).transpose(1, 2)
+    res["all_eps"] = torch.cat(res["all_eps"], dim=1).transpose(1, 2)
+    res["max"] = g.max()
+    return res

@@ -63,9 +63,9 @@ def save(name, **arrays):
           f"({os.path.getsize(path) / 1024:.1f} KiB)")
 
 
-def load_synth(module, seed):
+def load_synth(module, seed, gain=1.5):
     shapes = {k: tuple(v.shape) for k, v in module.state_dict().items()}
-    sd = O.synth_state_dict(shapes, seed)
+    sd = O.synth_state_dict(shapes, seed, gain)
     module.load_state_dict(sd, strict=True)
     return sd
 
@@ -138,6 +138,27 @@ def gen_condition():
             params_pts_only = model(x, t, condition={"pts": pts})
     save("condition.npz", img=img, pts=pts, x=x, t=t, pts_cond=pts_cond, img_cond=img_cond, params=params,
          params_pts_only=params_pts_only)
+
+
+def gen_encoder():
+    """Compressor.forward (bottom_up + top_down, Network.py:188-249) of the reference in eval mode; the un-vendored
+    pointnet2_ops FPS is replaced by the C oracle as in gen_condition()."""
+    from tests.helpers import oracle_fps
+    sys.modules["pointnet2_ops.pointnet2_utils"].furthest_point_sample = lambda xyz, m: oracle_fps(xyz, m)
+    from model.Compressor.Network import Compressor
+    cfg = dict2namespace(airplane_config()).compressor
+    torch.manual_seed(0)
+    comp = Compressor(cfg).eval()
+    load_synth(comp, 13, gain=0.6)   # 18 chained blocks with sharp 2048-key softmaxes: keep the map well conditioned
+    g = torch.Generator().manual_seed(213)
+    pts = torch.randn((2, 2048, 3), generator=g)
+    pts = pts / pts.norm(dim=-1).max(dim=1)[0][:, None, None]
+    with CudaToCpu(), torch.no_grad():
+        torch.manual_seed(6)
+        out = comp(pts)
+    save("encoder.npz", pts=pts, set=out["set"], all_eps=out["all_eps"], kls=torch.stack(out["kls"]),
+         mu=torch.stack([p[1] for p in out["posteriors"][1:]]), logvar=torch.stack([p[2] for p in out["posteriors"][1:]]),
+         max=out["max"])
 
 
 def gen_decoder():
@@ -281,6 +302,6 @@ def gen_nn():
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 1)
-    which = sys.argv[1:] or ["score", "unet", "condition", "decoder", "sde", "nn", "layout"]
+    which = sys.argv[1:] or ["score", "unet", "condition", "encoder", "decoder", "sde", "nn", "layout"]
     for w in which:
-        {"score": gen_score, "unet": gen_unet, "condition": gen_condition, "decoder": gen_decoder, "sde": gen_sde, "nn": gen_nn, "layout": gen_layout}[w]()
+        {"score": gen_score, "unet": gen_unet, "condition": gen_condition, "encoder": gen_encoder, "decoder": gen_decoder, "sde": gen_sde, "nn": gen_nn, "layout": gen_layout}[w]()

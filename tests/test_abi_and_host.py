@@ -87,8 +87,8 @@ def test_config_validation_mirrors_reference_errors():
         sde.sample_discrete(None, 1, 10, "nope", None, 1, (32, 120), 1e-6, False, True, 0.01, "cpu")
     with pytest.raises(NotImplementedError, match="corrector not Implemented"):
         sde.sample_discrete(None, 1, 10, "ancestral", "nope", 1, (32, 120), 1e-6, False, True, 0.01, "cpu")
-    with pytest.raises(NotImplementedError):
-        Compressor(cfg.compressor).forward(torch.zeros(1, 8, 3))
+    with pytest.raises(RuntimeError, match="CUDA"):   # no CPU fallback for the encoder path either
+        Compressor(cfg.compressor).forward(torch.zeros(1, 64, 3))
 
 
 def test_product_path_never_imports_oracle():

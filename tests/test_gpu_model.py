@@ -53,10 +53,10 @@ def build_score(cfg, seed, dev):
     return m.to(dev).eval(), sd
 
 
-def build_compressor(cfg, seed, dev):
+def build_compressor(cfg, seed, dev, gain=1.5):
     from ldt_b200 import Compressor
     m = Compressor(cfg)
-    sd = O.synth_state_dict(shapes_of(m), seed)
+    sd = O.synth_state_dict(shapes_of(m), seed, gain)
     m.load_state_dict(sd, strict=True)
     return m.to(dev).eval(), sd
 
@@ -458,3 +458,61 @@ def test_score_unet_vs_reference_golden_and_fused_loop(dev):
     generic = sde.sample_discrete(lambda t, x, label=None, condition=None: tr.score_fn(t, x), 4, 8, "ancestral", None, 1,
                                   (32, 120), 1e-6, False, True, 0.01, dev)
     assert rel_rms_err(fused, generic) < 1e-5, rel_rms_err(fused, generic)
+
+
+# ------------------------------------------------------------------------------------------------
+# Compressor.forward: encoder inference path
+# ------------------------------------------------------------------------------------------------
+def test_compressor_forward_vs_reference_golden(dev):
+    """bottom_up (FPS + k-NN grouping, AdaLN encoder blocks) + top_down (posterior blocks attending to the 2048 decoded
+    points, reparameterised latents from the CPU generator, decoder blocks) against the reference's own run."""
+    cfg = ns(airplane_config()).compressor
+    g = golden("encoder.npz")
+    comp, sd = build_compressor(cfg, 13, dev, gain=0.6)
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(6)
+        out = comp(g["pts"].to(dev))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert out["set"].shape == (2, 2048, 3) and out["all_eps"].shape == (2, 32, 120) and len(out["kls"]) == 6
+    assert len(out["posteriors"]) == 7 and out["posteriors"][0][1] is None
+    mu = torch.stack([p[1] for p in out["posteriors"][1:]])
+    check_vs_fp32(mu, g["mu"])
+    check_vs_fp32(out["all_eps"], g["all_eps"])
+    check_vs_fp32(out["set"], g["set"])
+    assert rms_rel_err(torch.stack(out["kls"]), g["kls"]) < 0.1
+    assert abs(float(out["max"]) - float(g["max"])) < 0.05 * abs(float(g["max"]))
+    # the CPU generator ends where the reference leaves it: B randperms + one randn per layer
+    torch.manual_seed(6)
+    O.sample_mask(2, 2048, cfg.max_outputs)
+    for _ in range(cfg.n_layers):
+        torch.randn((2, cfg.z_dim, cfg.z_scales))
+    want_state = torch.get_rng_state()
+    torch.manual_seed(6)
+    comp(g["pts"].to(dev))
+    assert torch.equal(torch.get_rng_state(), want_state)
+    # against the oracle with the same bf16 rounding points
+    torch.manual_seed(6)
+    from tests.helpers import oracle_fps
+    emu = emulated(lambda: O.compressor_forward(sd, cfg, g["pts"], oracle_fps))
+    assert rms_rel_err(out["all_eps"], emu["all_eps"]) < 2e-2, rms_rel_err(out["all_eps"], emu["all_eps"])
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk", [(2, 4, 32, 2048), (3, 4, 32, 1000), (1, 2, 5, 33)])
+def test_attention_longkv_vs_float64(dev, B, H, Nq, Nk):
+    from ldt_b200 import ops
+    dh = 32
+    g = torch.Generator().manual_seed(Nk)
+    q = torch.randn((B * Nq, H * dh), generator=g).to(dev).bfloat16()
+    kv = torch.randn((B * Nk, 2 * H * dh), generator=g).to(dev).bfloat16()
+    o = torch.empty((B * Nq, H * dh), dtype=torch.bfloat16, device=dev)
+    ops.attention_longkv(B, H, Nq, Nk, dh, q, H * dh, kv, torch.narrow(kv, 1, H * dh, H * dh), 2 * H * dh, o)
+    qd = q.double().view(B, Nq, H, dh).permute(0, 2, 1, 3)
+    kd = kv[:, :H * dh].double().view(B, Nk, H, dh).permute(0, 2, 1, 3)
+    vd = kv[:, H * dh:].double().view(B, Nk, H, dh).permute(0, 2, 1, 3)
+    w = torch.softmax(qd @ kd.transpose(-1, -2) * dh ** -0.5, dim=-1)
+    ref = (w @ vd).reshape(B * Nq, H * dh)          # [B,H,Nq,dh] contiguous, re-read token-major (layers.py:197)
+    assert_close = (o.double().cpu() - ref.cpu()).abs().max()
+    assert float(assert_close) < 2e-2, float(assert_close)

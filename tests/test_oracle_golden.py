@@ -345,3 +345,18 @@ def test_score_unet_oracle_and_layout_match_reference():
     sd = O.synth_state_dict({k: tuple(v) for k, v in lay.items()}, 19)
     assert rel_rms_err(O.score_forward_unet(sd, cfg, g["x"], g["t"]), g["params"]) < 1e-5
     assert rel_rms_err(O.score_forward_unet(sd, cfg, g["x"], g["t"], g["img_cond"]), g["params_cond"]) < 1e-5
+
+
+def test_compressor_forward_oracle_matches_reference():
+    """Compressor.forward (bottom_up + top_down): oracle vs the reference's own run (same CPU-generator draws)."""
+    from ldt_b200.compressor import compressor_param_spec
+    from tests.helpers import oracle_fps
+    cfg = ns(airplane_config()).compressor
+    g = golden("encoder.npz")
+    sd = O.synth_state_dict({k: v[0] for k, v in compressor_param_spec(cfg).items()}, 13, gain=0.6)
+    torch.manual_seed(6)
+    out = O.compressor_forward(sd, cfg, g["pts"], oracle_fps)
+    assert rel_rms_err(out["set"], g["set"]) < 1e-4
+    assert rel_rms_err(out["all_eps"], g["all_eps"]) < 1e-4
+    assert rel_rms_err(torch.stack(out["kls"]), g["kls"]) < 1e-3
+    assert abs(float(out["max"]) - float(g["max"])) < 1e-4 * abs(float(g["max"]))
