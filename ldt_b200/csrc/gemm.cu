@@ -707,7 +707,18 @@ static int launch_any(const ldt_gemm_args& a, const EpiParams& p, cudaStream_t s
   // backend 0 picks: CTA pairs (256-row tiles) once there are enough rows to fill them, else single-CTA tiles.
   const bool pair_ok = (a.backend == 3) || (a.backend == 0 && a.M >= 1024);
   if (pair_ok && a.backend != 2) {
-    if (a.N % 256 == 0) return launch_tc2<256, EPI>(a, p, s);
+    if (a.N % 256 == 0) {
+      // 256-wide tiles unless they leave most of the machine idle: at M = 2048 (64 clouds per GPU, the completion
+      // workload) an N = 1024 GEMM is 32 tiles for 74 CTA pairs; 128-wide tiles double the tile count at the same
+      // mainloop efficiency per column (A is re-read per tile either way)
+      const int pairs = num_sms() / 2;
+      const int tm = (a.M + T2_BM - 1) / T2_BM;
+      const int t256 = tm * (a.N / 256), t128 = tm * (a.N / 128);
+      const double u256 = static_cast<double>(t256) / (((t256 + pairs - 1) / pairs) * pairs);
+      const double u128 = static_cast<double>(t128) / (((t128 + pairs - 1) / pairs) * pairs);
+      if (u128 > u256 + 0.1) return launch_tc2<128, EPI>(a, p, s);
+      return launch_tc2<256, EPI>(a, p, s);
+    }
     return launch_tc2<128, EPI>(a, p, s);
   }
   if (a.N % 256 == 0) return launch_tc<256, EPI>(a, p, s);
