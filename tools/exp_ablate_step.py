@@ -1,0 +1,46 @@
+import os, sys
+sys.path.insert(0, "/root/repo")
+import torch
+from ldt_b200 import Score, ops
+from tests.helpers import airplane_config, ns
+dev = torch.device("cuda:0")
+B = 256
+model = Score(ns(airplane_config()).score).to(dev).eval()
+P = model.packed(); ws = model._workspace(B, 1, dev)
+x = torch.randn((B * 32, 120), device=dev); out = torch.empty_like(x)
+mod = torch.randn((1, ws.mod_len), device=dev) * 0.1
+real_ln, real_gemm, real_qkv = ops.layernorm_mod, ops.gemm, ops.qkv_attention
+def run(tag):
+    model.run_tokens(P, ws, x, mod, 0, out); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        model.run_tokens(P, ws, x, mod, 0, out)
+    for _ in range(20): g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(200): g.replay()
+    e1.record(); torch.cuda.synchronize()
+    print(f"{tag}: {e0.elapsed_time(e1)/200:.3f} ms per token pass", flush=True)
+run("full")
+ops.layernorm_mod = lambda *a, **k: None
+run("without LayerNorm launches")
+ops.layernorm_mod = real_ln
+def gemm_skip(A, W, bias, out_, epi, **k):
+    if epi == 3 and A.shape[1] == 1024: return out_
+    return real_gemm(A, W, bias, out_, epi, **k)
+ops.gemm = gemm_skip
+run("without fc_o")
+def gemm_skip2(A, W, bias, out_, epi, **k):
+    if epi == 3 and A.shape[1] == 4096: return out_
+    return real_gemm(A, W, bias, out_, epi, **k)
+ops.gemm = gemm_skip2
+run("without fc2")
+def gemm_skip3(A, W, bias, out_, epi, **k):
+    if epi == 2: return out_
+    return real_gemm(A, W, bias, out_, epi, **k)
+ops.gemm = gemm_skip3
+run("without fc1")
+ops.gemm = real_gemm
+ops.qkv_attention = lambda *a, **k: None
+run("without qkv_attention")
