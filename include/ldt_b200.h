@@ -152,14 +152,15 @@ int ldt_time_embedding(int R, int half, int D, const float* t, const float* freq
  *   o  bf16: written as the reference's (w@v).reshape(B,N,C) does (layers.py:197): the [B,H,Nq,dh]
  *      result buffer is stored contiguously and re-read as token-major [B*Nq, H*dh] WITHOUT permuting
  *      heads back.  This quirk is part of the trained weights' meaning and is reproduced on purpose.
- * Nk must be 32 (z_scale latent tokens); dh in {32, 64}. */
+ * Nk must be 32 (z_scale latent tokens); dh in {8, 16, 32, 64} (8 / 16: the 128-wide, 16-head score net of
+ * experiments/Hybrid_Trainer/airplane/config.yaml, served by a one-lane-per-query SIMT kernel). */
 int ldt_attention_nk32(int B, int H, int Nq, int dh, const void* q, int ldq, const void* k, const void* v,
                        int ldkv, void* o, void* stream);
 
 /* The transposed shape: a SHORT query set over a LONG key set (Nq = 32 latent tokens attending to the Nk = 2048 decoded
  * points in DecoderBlock.compute_posterior, model/Compressor/Network.py:62-77), online softmax over key chunks.
  * Same operand and output layouts as ldt_attention_nk32 (q [B*Nq, ldq], k/v [B*Nk, ldkv], o = [B,H,Nq,dh] contiguous).
- * dh must be 32. */
+ * dh in {32, 64}. */
 int ldt_attention_longkv(int B, int H, int Nq, int Nk, int dh, const void* q, int ldq, const void* k, const void* v,
                          int ldkv, void* o, void* stream);
 

@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(ATTL_WARPS * 32)
 attention_longkv_kernel(int H, int Nq, int Nk, const __nv_bfloat16* __restrict__ q, int ldq,
                         const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v, int ldkv,
                         __nv_bfloat16* __restrict__ o, float scale_log2e) {
-  static_assert(DH == 32, "one output channel per lane");
+  static_assert(DH == 32 || DH == 64, "lane d owns output channels d, d + 32, ...");
+  constexpr int CPL = DH / 32;   // output channels per lane
   __shared__ float Ks[32][DH + 1], Vs[32][DH + 1], Qs[ATTL_WARPS][DH];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qblocks = (Nq + ATTL_WARPS - 1) / ATTL_WARPS;
@@ -185,8 +186,14 @@ attention_longkv_kernel(int H, int Nq, int Nk, const __nv_bfloat16* __restrict__
   const int h = bh % H, b = bh / H;
   const int qi = qb * ATTL_WARPS + warp;
   const bool live = qi < Nq;
-  if (live) Qs[warp][lane] = __bfloat162float(q[(static_cast<size_t>(b) * Nq + qi) * ldq + h * DH + lane]);
-  float m = -INFINITY, l = 0.f, acc = 0.f;
+  if (live) {
+#pragma unroll
+    for (int c = 0; c < CPL; ++c)
+      Qs[warp][lane + 32 * c] = __bfloat162float(q[(static_cast<size_t>(b) * Nq + qi) * ldq + h * DH + lane + 32 * c]);
+  }
+  float m = -INFINITY, l = 0.f, acc[CPL];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) acc[c] = 0.f;
   for (int k0 = 0; k0 < Nk; k0 += 32) {
     __syncthreads();   // previous chunk fully consumed
     for (int i = threadIdx.x; i < 32 * DH; i += ATTL_WARPS * 32) {
@@ -209,13 +216,81 @@ attention_longkv_kernel(int H, int Nq, int Nk, const __nv_bfloat16* __restrict__
       const float corr = exp2f(m - m_new);          // first chunk: exp2(-inf) = 0
       const float pj = exp2f(sc - m_new);
       l = l * corr + warp_sum(pj);
-      acc *= corr;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc = fmaf(__shfl_sync(0xffffffffu, pj, j), Vs[j][lane], acc);
+      for (int c = 0; c < CPL; ++c) acc[c] *= corr;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float pb = __shfl_sync(0xffffffffu, pj, j);
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) acc[c] = fmaf(pb, Vs[j][lane + 32 * c], acc[c]);
+      }
       m = m_new;
     }
   }
-  if (live) o[((static_cast<size_t>(b) * H + h) * Nq + qi) * DH + lane] = __float2bfloat16_rn(acc / l);
+  if (live) {
+#pragma unroll
+    for (int c = 0; c < CPL; ++c)
+      o[((static_cast<size_t>(b) * H + h) * Nq + qi) * DH + lane + 32 * c] = __float2bfloat16_rn(acc[c] / l);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Narrow heads (head dim 8 or 16: the Hybrid trainer's score net is 128 wide with 16 heads,
+// experiments/Hybrid_Trainer/airplane/config.yaml:53-54) over the 32 latent tokens: the mma.sync tiles above need a
+// contraction of at least 16 per instruction and would run 3/4 empty, so one lane per query row does the whole row in
+// registers (32 scores, DH outputs); K and V of the (batch, head) live in shared memory.  Same layouts as above.
+// ------------------------------------------------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attention_nk32_narrow_kernel(int units, int H, int Nq, int qtiles, const __nv_bfloat16* __restrict__ q, int ldq,
+                             const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v, int ldkv,
+                             __nv_bfloat16* __restrict__ o, float scale_log2e) {
+  __shared__ float Ks[ATT_WARPS][32][DH + 1], Vs[ATT_WARPS][32][DH + 1];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * ATT_WARPS + warp;
+  if (unit >= units) return;
+  const int qt = unit % qtiles;
+  const int bh = unit / qtiles;
+  const int h = bh % H, b = bh / H;
+#pragma unroll
+  for (int d = 0; d < DH; ++d) {   // lane = key
+    Ks[warp][lane][d] = __bfloat162float(k[(static_cast<size_t>(b) * 32 + lane) * ldkv + h * DH + d]);
+    Vs[warp][lane][d] = __bfloat162float(v[(static_cast<size_t>(b) * 32 + lane) * ldkv + h * DH + d]);
+  }
+  __syncwarp();
+  const int qi = qt * 32 + lane;
+  if (qi >= Nq) return;
+  float qr[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) qr[d] = __bfloat162float(q[(static_cast<size_t>(b) * Nq + qi) * ldq + h * DH + d]);
+  float sc[32], mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float a = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) a = fmaf(qr[d], Ks[warp][j][d], a);
+    sc[j] = a * scale_log2e;
+    mx = fmaxf(mx, sc[j]);
+  }
+  float sum = 0.f, out[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) out[d] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float e = exp2f(sc[j] - mx);
+    sum += e;
+    // the wide-head kernel rounds the un-normalised probabilities to bf16 before the PV product; keep the same
+    // rounding point for both head widths (the parity tests emulate it)
+    const float p = __bfloat162float(__float2bfloat16_rn(e));
+#pragma unroll
+    for (int d = 0; d < DH; ++d) out[d] = fmaf(p, Vs[warp][j][d], out[d]);
+  }
+  const float inv = 1.0f / sum;
+  __nv_bfloat16* op = o + ((static_cast<size_t>(b) * H + h) * Nq + qi) * DH;
+#pragma unroll
+  for (int d = 0; d < DH; ++d) op[d] = __float2bfloat16_rn(out[d] * inv);
 }
 
 }  // namespace ldt
@@ -225,7 +300,7 @@ using namespace ldt;
 extern "C" int ldt_attention_nk32(int B, int H, int Nq, int dh, const void* q, int ldq, const void* k, const void* v,
                                   int ldkv, void* o, void* stream) {
   LDT_REQUIRE(B >= 0 && H > 0 && Nq > 0, LDT_ERR_INVALID, "ldt_attention_nk32: bad shape B=%d H=%d Nq=%d", B, H, Nq);
-  LDT_REQUIRE(dh == 32 || dh == 64, LDT_ERR_UNSUPPORTED, "ldt_attention_nk32: head dim %d not in {32,64}", dh);
+  LDT_REQUIRE(dh == 8 || dh == 16 || dh == 32 || dh == 64, LDT_ERR_UNSUPPORTED, "ldt_attention_nk32: head dim %d not in {8,16,32,64}", dh);
   if (B == 0) return LDT_OK;
   LDT_REQUIRE(q && k && v && o, LDT_ERR_INVALID, "ldt_attention_nk32: null pointer");
   LDT_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && ldq >= H * dh && ldkv >= H * dh, LDT_ERR_INVALID,
@@ -239,6 +314,18 @@ extern "C" int ldt_attention_nk32(int B, int H, int Nq, int dh, const void* q, i
   const int grid = static_cast<int>((units + ATT_WARPS - 1) / ATT_WARPS);
   const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(dh));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dh == 8 || dh == 16) {
+    auto* qq = static_cast<const __nv_bfloat16*>(q);
+    auto* kk = static_cast<const __nv_bfloat16*>(k);
+    auto* vv = static_cast<const __nv_bfloat16*>(v);
+    auto* oo = static_cast<__nv_bfloat16*>(o);
+    if (dh == 8)
+      attention_nk32_narrow_kernel<8><<<grid, ATT_WARPS * 32, 0, s>>>(static_cast<int>(units), H, Nq, qtiles, qq, ldq, kk, vv, ldkv, oo, scale_log2e);
+    else
+      attention_nk32_narrow_kernel<16><<<grid, ATT_WARPS * 32, 0, s>>>(static_cast<int>(units), H, Nq, qtiles, qq, ldq, kk, vv, ldkv, oo, scale_log2e);
+    LDT_CUDA_OK(cudaGetLastError());
+    return LDT_OK;
+  }
   if (dh == 64)
     attention_nk32_kernel<64><<<grid, ATT_WARPS * 32, 0, s>>>(static_cast<int>(units), H, Nq, qtiles,
                                                              static_cast<const __nv_bfloat16*>(q), ldq,
@@ -259,16 +346,21 @@ extern "C" int ldt_attention_longkv(int B, int H, int Nq, int Nk, int dh, const 
                                     int ldkv, void* o, void* stream) {
   LDT_REQUIRE(B >= 0 && H > 0 && Nq > 0 && Nk > 0, LDT_ERR_INVALID, "ldt_attention_longkv: bad shape B=%d H=%d Nq=%d Nk=%d", B, H,
               Nq, Nk);
-  LDT_REQUIRE(dh == 32, LDT_ERR_UNSUPPORTED, "ldt_attention_longkv: head dim %d not supported (32 only)", dh);
+  LDT_REQUIRE(dh == 32 || dh == 64, LDT_ERR_UNSUPPORTED, "ldt_attention_longkv: head dim %d not in {32,64}", dh);
   if (B == 0) return LDT_OK;
   LDT_REQUIRE(q && k && v && o, LDT_ERR_INVALID, "ldt_attention_longkv: null pointer");
   LDT_REQUIRE(ldq >= H * dh && ldkv >= H * dh, LDT_ERR_INVALID, "ldt_attention_longkv: ldq=%d ldkv=%d must be >= H*dh", ldq, ldkv);
   const long long blocks = static_cast<long long>(B) * H * ((Nq + ATTL_WARPS - 1) / ATTL_WARPS);
   LDT_REQUIRE(blocks < (1LL << 31), LDT_ERR_INVALID, "ldt_attention_longkv: too many work units");
   const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(dh));
-  attention_longkv_kernel<32><<<static_cast<int>(blocks), ATTL_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      H, Nq, Nk, static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k),
-      static_cast<const __nv_bfloat16*>(v), ldkv, static_cast<__nv_bfloat16*>(o), scale_log2e);
+  if (dh == 32)
+    attention_longkv_kernel<32><<<static_cast<int>(blocks), ATTL_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        H, Nq, Nk, static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k),
+        static_cast<const __nv_bfloat16*>(v), ldkv, static_cast<__nv_bfloat16*>(o), scale_log2e);
+  else
+    attention_longkv_kernel<64><<<static_cast<int>(blocks), ATTL_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        H, Nq, Nk, static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k),
+        static_cast<const __nv_bfloat16*>(v), ldkv, static_cast<__nv_bfloat16*>(o), scale_log2e);
   LDT_CUDA_OK(cudaGetLastError());
   return LDT_OK;
 }

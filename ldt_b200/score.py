@@ -148,8 +148,8 @@ class Score(nn.Module):
             raise NotImplementedError("ldt_b200.Score: only norm: layer_norm (the shipped configs) is supported")
         if self.dropout != 0:
             raise NotImplementedError("ldt_b200.Score is a sampling path: dropout must be 0")
-        if self.hidden_size % 128 != 0 or self.hidden_size // self.num_heads not in (32, 64) or self.z_scale != 32:
-            raise NotImplementedError("ldt_b200.Score: needs hidden_size % 128 == 0, head dim 32 or 64, z_scale 32")
+        if self.hidden_size % 128 != 0 or self.hidden_size // self.num_heads not in (8, 16, 32, 64) or self.z_scale != 32:
+            raise NotImplementedError("ldt_b200.Score: needs hidden_size % 128 == 0, head dim in {8, 16, 32, 64}, z_scale 32")
         # construction order follows score.py:65-97 (condition net, blocks, label embedding, ln_in, time embedding,
         # final layer)
         if self.condition:

@@ -333,7 +333,8 @@ def test_time_embedding_vs_oracle(dev):
     assert rel_rms_err(c, ref + extra) < 1e-5
 
 
-@pytest.mark.parametrize("B,H,Nq,dh", [(3, 16, 32, 64), (2, 4, 2048, 32), (2, 4, 1000, 32), (5, 2, 32, 64)])
+@pytest.mark.parametrize("B,H,Nq,dh", [(3, 16, 32, 64), (2, 4, 2048, 32), (2, 4, 1000, 32), (5, 2, 32, 64),
+                                       (3, 16, 32, 8), (2, 8, 32, 16), (2, 16, 100, 8)])
 def test_attention_with_reference_layout_quirk(dev, B, H, Nq, dh):
     from ldt_b200 import ops
     C_ = H * dh

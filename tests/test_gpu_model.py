@@ -500,10 +500,9 @@ def test_compressor_forward_vs_reference_golden(dev):
     assert rms_rel_err(out["all_eps"], emu["all_eps"]) < 2e-2, rms_rel_err(out["all_eps"], emu["all_eps"])
 
 
-@pytest.mark.parametrize("B,H,Nq,Nk", [(2, 4, 32, 2048), (3, 4, 32, 1000), (1, 2, 5, 33)])
-def test_attention_longkv_vs_float64(dev, B, H, Nq, Nk):
+@pytest.mark.parametrize("B,H,Nq,Nk,dh", [(2, 4, 32, 2048, 32), (3, 4, 32, 1000, 32), (1, 2, 5, 33, 32), (2, 4, 32, 700, 64)])
+def test_attention_longkv_vs_float64(dev, B, H, Nq, Nk, dh):
     from ldt_b200 import ops
-    dh = 32
     g = torch.Generator().manual_seed(Nk)
     q = torch.randn((B * Nq, H * dh), generator=g).to(dev).bfloat16()
     kv = torch.randn((B * Nk, 2 * H * dh), generator=g).to(dev).bfloat16()
@@ -516,3 +515,43 @@ def test_attention_longkv_vs_float64(dev, B, H, Nq, Nk):
     ref = (w @ vd).reshape(B * Nq, H * dh)          # [B,H,Nq,dh] contiguous, re-read token-major (layers.py:197)
     assert_close = (o.double().cpu() - ref.cpu()).abs().max()
     assert float(assert_close) < 2e-2, float(assert_close)
+
+
+# ------------------------------------------------------------------------------------------------
+# the other shipped / default configurations of the reference
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,over", [
+    ("hybrid", dict(hidden_size=128, num_heads=16, t_dim=128, num_blocks=3)),     # experiments/Hybrid_Trainer/airplane/config.yaml:49-65 (head dim 8)
+    ("t_dim != hidden", dict(hidden_size=128, num_heads=2, t_dim=256, num_blocks=2)),
+    ("scorenet default", dict(hidden_size=256, num_heads=4, t_dim=128, num_blocks=4, unet=True)),   # model/scorenet/config.yaml shape family (unet, t_dim != hidden)
+])
+def test_score_other_reference_configs_vs_oracle(dev, name, over):
+    cfg = ns(airplane_config()).score
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    model, sd = build_score(cfg, 23, dev)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((5, 32, 120), generator=g)
+    t = torch.rand((5,), generator=g) * 0.98 + 0.01
+    fwd = O.score_forward_unet if cfg.unet else O.score_forward
+    ref = fwd(sd, cfg, x, t)
+    with torch.no_grad():
+        out = model(x.to(dev), t.to(dev))
+    check_vs_fp32(out, ref)
+    emu = emulated(lambda: fwd(sd, cfg, x, t))
+    assert rms_rel_err(out, emu) < TOL_RMS_EMUL, (name, rms_rel_err(out, emu))
+
+
+def test_decoder_default_compressor_config_vs_oracle(dev):
+    """model/Compressor/config.yaml: hidden_dim 256, 4 heads (head dim 64), pos_embedding mlp -- sampling decoder."""
+    cfg = ns(airplane_config()).compressor
+    cfg.hidden_dim, cfg.pos_embedding = 256, "mlp"
+    comp, sd = build_compressor(cfg, 29, dev)
+    g = torch.Generator().manual_seed(6)
+    eps = torch.randn((2, cfg.z_scales, cfg.n_layers * cfg.z_dim), generator=g)
+    torch.manual_seed(3)
+    ref = O.decoder_sample(sd, cfg, eps, 2048)
+    torch.manual_seed(3)
+    with torch.no_grad():
+        pts = comp.sample((2, 2048), given_eps=eps.to(dev))
+    check_vs_fp32(pts, ref)
