@@ -116,6 +116,10 @@ int ldt_gemm_bf16(const ldt_gemm_args* args, void* stream);
  * stage, [6] producer total, [7] tiles.  dev_buf must hold 8 * gridDim u64 (<= 8 * SM count).  NULL switches it off. */
 int ldt_debug_set_gemm_counters(unsigned long long* dev_buf);
 
+/* Diagnostics (tools/exp_gemm_limits.py only; results are WRONG while set): bit 0 = the CTA-pair GEMM skips its A
+ * loads, bit 1 = skips its W loads (half the operand traffic either way), bit 2 = skips the epilogue.  0 = off. */
+int ldt_debug_set_gemm_mode(int mode);
+
 /* ------------------------------------------------------------------------------------------------
  * Element-wise / normalisation kernels of the score net and decoder
  * ------------------------------------------------------------------------------------------------ */

@@ -60,6 +60,7 @@ PROTOTYPES = {
                                    C.c_void_p]),
     "ldt_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "ldt_debug_set_gemm_counters": (C.c_int, [C.c_void_p]),
+    "ldt_debug_set_gemm_mode": (C.c_int, [C.c_int]),
     "ldt_cast_pad_bf16": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "ldt_pack_weights": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "ldt_layernorm_mod_bf16": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,
