@@ -110,6 +110,35 @@ typedef struct ldt_gemm_args {
 
 int ldt_gemm_bf16(const ldt_gemm_args* args, void* stream);
 
+/* Fused MLP half of a transformer block, one launch:
+ *     out[M,C] = resid + gate * ( GELU(A[M,C] . W1[inner,C]^T + bias1) . W2[C,inner]^T + bias2 )
+ * = MLP.forward (model/layers.py:110-133: Conv1d(C->4C), nn.GELU() exact erf, Conv1d(4C->C)) followed by the gated
+ * residual add of ResidualBlock.forward (layers.py:219); bit-identical to ldt_gemm_bf16(LDT_EPI_BIAS_GELU_BF16) followed by
+ * ldt_gemm_bf16(LDT_EPI_GATE_RESID_F32).  fc2 tiles start as soon as the fc1 tiles of their 256 rows are stored.
+ *   A, W1, W2 bf16 row-major; `hidden` = caller-owned bf16 scratch [M, ldh >= inner] (the GELU output lives there);
+ *   resid/out f32 [M, ldo] (may alias); gate as in ldt_gemm_args (NULL = 1).
+ *   sync = caller-owned device words, ldt_mlp_sync_words(M) of them, ZEROED ONCE before the first call: per-256-row
+ *   completion counters.  The kernel leaves them zero again (self-cleaning), so the same buffer serves every later
+ *   launch on the same stream; two launches in flight at once need two buffers.
+ *   Needs C % 256 == 0 and inner % 256 == 0 (LDT_ERR_UNSUPPORTED otherwise: use the two GEMM calls) and a grid of
+ *   co-resident CTA pairs (checked with cudaOccupancyMaxActiveClusters). */
+typedef struct {
+  int M, C, inner;
+  const void* A;      int lda;
+  const void* W1;     int ldw1;   const float* bias1;
+  void* hidden;       int ldh;
+  const void* W2;     int ldw2;   const float* bias2;
+  const float* resid; float* out; int ldo;
+  const float* gate;  long long gate_stride; int rows_per_gate;
+  unsigned int* sync;
+} ldt_mlp_args;
+int ldt_mlp_bf16(const ldt_mlp_args* args, void* stream);
+int ldt_mlp_sync_words(int M);
+/* The kernel's static tile schedule, host-side (tests): work item `it` of CTA pair `p` of `pairs`; *phase = 1 (fc1 tile),
+ * 2 (fc2 tile) or 0 (surplus slot / out of range), with its 256-row block and 256-column tile. */
+int ldt_mlp_schedule_item(int tiles_m, int tn1, int tn2, int kb1, int kb2, int pairs, int p, int it, int* num_items,
+                          int* phase, int* mb, int* nt);
+
 /* Diagnostics: when dev_buf != NULL, every CTA of the CTA-pair GEMM kernel writes 8 u64 stall counters
  * (clock64 ticks) at dev_buf[8*blockIdx.x ...]: [0] MMA thread total, [1] its wait for TMA data, [2] its wait for
  * a free accumulator, [3] epilogue warp total, [4] its wait for the accumulator, [5] TMA producer wait for a free
@@ -117,8 +146,11 @@ int ldt_gemm_bf16(const ldt_gemm_args* args, void* stream);
 int ldt_debug_set_gemm_counters(unsigned long long* dev_buf);
 
 /* Diagnostics (tools/exp_gemm_limits.py only; results are WRONG while set): bit 0 = the CTA-pair GEMM skips its A
- * loads, bit 1 = skips its W loads (half the operand traffic either way), bit 2 = skips the epilogue.  0 = off. */
+ * loads, bit 1 = skips its W loads (half the operand traffic either way), bit 2 = skips the epilogue, bit 3 = the fused
+ * MLP kernel ignores its completion counters, bits 3-6 (with the counters on, GELU epilogue) = epilogue parts removed,
+ * bit 8 = bf16 outputs through per-lane st.global instead of bulk tensor stores (results stay correct).  0 = off. */
 int ldt_debug_set_gemm_mode(int mode);
+int ldt_debug_get_gemm_mode(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Element-wise / normalisation kernels of the score net and decoder

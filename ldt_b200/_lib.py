@@ -42,6 +42,19 @@ class GemmArgs(C.Structure):
     ]
 
 
+class MlpArgs(C.Structure):
+    _fields_ = [
+        ("M", C.c_int), ("C", C.c_int), ("inner", C.c_int),
+        ("A", C.c_void_p), ("lda", C.c_int),
+        ("W1", C.c_void_p), ("ldw1", C.c_int), ("bias1", C.c_void_p),
+        ("hidden", C.c_void_p), ("ldh", C.c_int),
+        ("W2", C.c_void_p), ("ldw2", C.c_int), ("bias2", C.c_void_p),
+        ("resid", C.c_void_p), ("out", C.c_void_p), ("ldo", C.c_int),
+        ("gate", C.c_void_p), ("gate_stride", C.c_longlong), ("rows_per_gate", C.c_int),
+        ("sync", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); the single source of truth used by tests to check exported symbols
 PROTOTYPES = {
     "ldt_abi_version": (C.c_int, []),
@@ -59,8 +72,12 @@ PROTOTYPES = {
     "ldt_pairwise_emd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                    C.c_void_p]),
     "ldt_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "ldt_mlp_bf16": (C.c_int, [C.POINTER(MlpArgs), C.c_void_p]),
+    "ldt_mlp_sync_words": (C.c_int, [C.c_int]),
+    "ldt_mlp_schedule_item": (C.c_int, [C.c_int] * 8 + [C.POINTER(C.c_int)] * 4),
     "ldt_debug_set_gemm_counters": (C.c_int, [C.c_void_p]),
     "ldt_debug_set_gemm_mode": (C.c_int, [C.c_int]),
+    "ldt_debug_get_gemm_mode": (C.c_int, []),
     "ldt_cast_pad_bf16": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "ldt_pack_weights": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "ldt_layernorm_mod_bf16": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,

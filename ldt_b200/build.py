@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(CSRC, "libldt_b200.so")
-SOURCES = ["api.cu", "nn_distance.cu", "gemm.cu", "elementwise.cu", "attention.cu", "qkv_attention.cu", "emd.cu", "pointops.cu"]
+SOURCES = ["api.cu", "nn_distance.cu", "gemm.cu", "mlp.cu", "elementwise.cu", "attention.cu", "qkv_attention.cu", "emd.cu", "pointops.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -38,6 +38,27 @@ def needs_build() -> bool:
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
     deps.append(os.path.join(INCLUDE, "ldt_b200.h"))
     return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_variant(tag: str, defines: list[str]) -> str:
+    """Build ``libldt_b200_<tag>.so`` with extra ``-D`` defines (A/B experiments of kernel variants, tools/exp_ab_lib.py)."""
+    nvcc = _nvcc()
+    objdir = os.path.join(CSRC, "build", tag)
+    os.makedirs(objdir, exist_ok=True)
+    out = os.path.join(CSRC, f"libldt_b200_{tag}.so")
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        r = subprocess.run([nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        objs.append(obj)
+    r = subprocess.run([nvcc, "-shared", "-o", out, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return out
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

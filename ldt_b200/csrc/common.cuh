@@ -142,6 +142,21 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// 2-D tiled TMA STORE of one box from this CTA's shared memory (bulk async-group completion).  Rows / columns outside
+// the tensor are clipped by the hardware.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of this thread's bulk groups have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have completed altogether (the global writes are performed)
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes to shared memory made visible to the async proxy (TMA store source)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ---- tcgen05 / TMEM ---------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
@@ -227,6 +242,17 @@ __device__ __forceinline__ void tma_load_2d_pair_u32(uint32_t smem_dst, const vo
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// The same, multicast: the box lands at the same shared-memory offset in every CTA of `cta_mask`, and each destination
+// CTA's bytes are signalled on the barrier at `bar`'s offset in the LEADER (even) CTA of that destination's pair (the
+// address must have the pair's peer bit clear, e.g. mapa to an even rank).
+__device__ __forceinline__ void tma_load_2d_pair_mcast_u32(uint32_t smem_dst, const void* tmap, uint32_t bar_cluster_addr,
+                                                           int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {  // one warp in EACH CTA of the pair
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
                "r"(ncols)
@@ -302,12 +328,16 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
 // exact-erf GELU (nn.GELU() default, reference tools/utils.py:107-108)
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-// The same function for GEMM epilogues, branch-free: erf by Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, i.e.
-// below fp32 resolution of 1+erf and 3 orders below the bf16 rounding applied to the result), 2 MUFU + 11 FP32 ops
-// instead of erff's two divergent branches.
+// The same function for GEMM epilogues, branch-free and with ONE special-function op per element.  The epilogue of the
+// fc1 GEMM is bound by the MUFU pipe (16 lanes/clk/SM: a warp-wide MUFU occupies its scheduler's share for 8 cycles), so
+// the form matters more than the FP32 count:
+//     gelu(x) = max(x, 0) - |x/2| * erfc(|x| / sqrt(2)),      erfc(|x| / sqrt(2)) = 2^q(|x|),
+// q = degree-7 fit of log2(erfc(a / sqrt(2))) on a in [0, 5.6] (weighted for absolute error of erfc); beyond 5.6 erfc
+// < 2.2e-8 and the argument is clamped.  fp32 Horner + ex2.approx: |abs error| <= 3.7e-7, relative error <= 3.1e-5
+// wherever |gelu| > 1e-3 (the Abramowitz-Stegun 7.1.26 form it replaces: 2.1e-7 / 1.7e-4, with rcp + ex2) -- two orders
+// below the bf16 rounding applied to the result.  1 MUFU + 11 FP32-pipe ops.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-  // z = x / sqrt(2) never materialises: |z| enters through pre-scaled constants, and the sign through |x/2|:
-  //   gelu(x) = x/2 + |x/2| * erf(|z|)       (erf odd)
+#ifdef LDT_GELU_AS   // A/B builds only: the Abramowitz-Stegun 7.1.26 form (rcp + ex2) this replaced
   float t, e;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.0f)));
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
@@ -316,9 +346,21 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   poly = fmaf(poly, t, 0.254829592f);
   poly *= t;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((x * x) * (-0.5f * 1.4426950408889634f)));
-  const float erf_abs = fmaf(-poly, e, 1.0f);
-  const float hx = 0.5f * x;
-  return fmaf(fabsf(hx), erf_abs, hx);
+  const float hx0 = 0.5f * x;
+  return fmaf(fabsf(hx0), fmaf(-poly, e, 1.0f), hx0);
+#else
+  const float a = fminf(fabsf(x), 5.6f);
+  float q = fmaf(7.732903964e-06f, a, -4.679716980e-05f);
+  q = fmaf(q, a, -4.473918779e-04f);
+  q = fmaf(q, a, 7.435896264e-03f);
+  q = fmaf(q, a, -5.273329248e-02f);
+  q = fmaf(q, a, -4.591345845e-01f);
+  q = fmaf(q, a, -1.151114419e+00f);
+  q = fmaf(q, a, 3.068670393e-07f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
+  return fmaf(-fabsf(0.5f * x), e, fmaxf(x, 0.0f));
+#endif
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);

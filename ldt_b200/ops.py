@@ -9,7 +9,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_GATE_RESID_F32, GemmArgs, check, load,
+from ._lib import (EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_GATE_RESID_F32, GemmArgs, MlpArgs, check, load,
                    ptr, stream_ptr)
 
 
@@ -170,6 +170,36 @@ def gemm(A: torch.Tensor, W: torch.Tensor, bias, out: torch.Tensor, epilogue: in
                     gate_stride=gate_stride, rows_per_gate=rows_per_gate, backend=backend)
     with torch.cuda.device(A.device), _launch("gemm", 1, (M, N, K, epilogue)):
         check(load().ldt_gemm_bf16(C.byref(args), stream_ptr()), "ldt_gemm_bf16")
+    return out
+
+
+def mlp_sync_buffer(M: int, device) -> torch.Tensor:
+    """Zeroed per-256-row completion counters for :func:`mlp` (self-cleaning: allocate once per workspace)."""
+    return torch.zeros((load().ldt_mlp_sync_words(M),), dtype=torch.int32, device=device)
+
+
+def mlp_supported(M: int, Cc: int, inner: int) -> bool:
+    """Shapes the fused MLP kernel takes (whole 256-wide tiles; enough rows to fill CTA pairs)."""
+    return M >= 1024 and Cc % 256 == 0 and inner % 256 == 0
+
+
+def mlp(A: torch.Tensor, W1: torch.Tensor, b1, hidden: torch.Tensor, W2: torch.Tensor, b2, out: torch.Tensor, sync: torch.Tensor,
+        *, resid=None, gate=None, gate_stride: int = 0, rows_per_gate: int = 1) -> torch.Tensor:
+    """out = resid + gate * (GELU(A @ W1.T + b1) @ W2.T + b2) in one launch (MLP + gated residual, layers.py:110-133,219).
+    A bf16 [M, C]; W1 bf16 [inner, C]; hidden bf16 [M, inner] scratch; W2 bf16 [C, inner]; out/resid f32 [M, C]."""
+    assert A.dtype == torch.bfloat16 and W1.dtype == torch.bfloat16 and W2.dtype == torch.bfloat16
+    assert hidden.dtype == torch.bfloat16 and out.dtype == torch.float32 and sync.dtype == torch.int32
+    M, Cc = A.shape
+    inner = W1.shape[0]
+    assert W2.shape[0] == Cc and hidden.shape[0] >= M and hidden.shape[1] >= inner
+    assert sync.numel() >= load().ldt_mlp_sync_words(M)
+    resid = out if resid is None else resid
+    args = MlpArgs(M=M, C=Cc, inner=inner, A=ptr(A), lda=A.stride(0), W1=ptr(W1), ldw1=W1.stride(0), bias1=ptr(b1),
+                   hidden=ptr(hidden), ldh=hidden.stride(0), W2=ptr(W2), ldw2=W2.stride(0), bias2=ptr(b2),
+                   resid=ptr(resid), out=ptr(out), ldo=out.stride(0), gate=ptr(gate), gate_stride=gate_stride,
+                   rows_per_gate=rows_per_gate, sync=ptr(sync))
+    with torch.cuda.device(A.device), _launch("mlp", 1, (M, Cc, inner)):
+        check(load().ldt_mlp_bf16(C.byref(args), stream_ptr()), "ldt_mlp_bf16")
     return out
 
 

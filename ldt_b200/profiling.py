@@ -35,7 +35,7 @@ def profile_score_step(score, B: int, reps: int = 3) -> dict:
                 key = kind if kind != "gemm" else f"gemm N={note[1]} K={note[2]}"
                 by_kind[key] = by_kind.get(key, 0.0) + ms / reps
                 total_ms += ms / reps
-                if kind in ("gemm", "qkv_attention"):   # the tcgen05 contraction kernels
+                if kind in ("gemm", "qkv_attention", "mlp"):   # the tcgen05 contraction kernels
                     gemm_ms += ms / reps
                     gemm_launches += 1
                 if kind == "qkv_attention":

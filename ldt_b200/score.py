@@ -112,6 +112,7 @@ class _Workspace:
         self.qkv = torch.empty((M, 3 * hidden), dtype=bf, device=device)
         self.att = torch.empty((M, hidden), dtype=bf, device=device)
         self.hid = torch.empty((M, 4 * hidden), dtype=bf, device=device)
+        self.mlp_sync = ops.mlp_sync_buffer(M, device)   # completion counters of the fused MLP kernel (self-cleaning)
         self.t_dim = hidden if t_dim is None else t_dim
         self.set_mod_rows(mod_rows, hidden, half, device)
 
@@ -177,6 +178,9 @@ class Score(nn.Module):
         # self-attention blocks run the fused projection+attention kernel (head dim 64, 32 tokens); False selects the
         # unfused GEMM + attention kernels (kept for cross-attention blocks and as a cross-check in the tests)
         self.fused_attention = True
+        # the MLP half of a block (fc1 + GELU -> fc2 + gate + residual) runs as ONE persistent kernel when the shapes fill
+        # whole CTA-pair tiles (ops.mlp_supported); False selects the two GEMM launches (bit-identical, kept as cross-check)
+        self.fused_mlp = True
 
     # ------------------------------------------------------------------------------------------
     # weight packing (fp32 parameters -> bf16 K-major GEMM operands), invalidated when any parameter's
@@ -282,6 +286,17 @@ class Score(nn.Module):
         ops.gemm(ws.sc, P["w_ada"], P["b_ada"], ws.mod, EPI_BIAS_F32)
         return ws.mod
 
+    def _mlp(self, ws, W, gate, mod_stride, T):
+        """ws.h += gate * MLP(ws.a)  (layers.py:219 with MLP.forward :110-133)."""
+        w1, w2 = W["w_fc1"], W["w_fc2"]
+        if self.fused_mlp and ops.mlp_supported(ws.M, w2.shape[0], w1.shape[0]):
+            ops.mlp(ws.a, w1, W["b_fc1"], ws.hid, w2, W["b_fc2"], ws.h, ws.mlp_sync, resid=ws.h, gate=gate,
+                    gate_stride=mod_stride, rows_per_gate=T)
+            return
+        ops.gemm(ws.a, w1, W["b_fc1"], ws.hid, EPI_BIAS_GELU_BF16)
+        ops.gemm(ws.hid, w2, W["b_fc2"], ws.h, EPI_GATE_RESID_F32, resid=ws.h, gate=gate, gate_stride=mod_stride,
+                 rows_per_gate=T)
+
     def run_tokens(self, P, ws, x_tokens, mod, mod_stride, out, kv_cond=None):
         """The per-step token path: x_tokens f32 [M, z_dim] -> out f32 [M, z_dim].  ``mod`` holds the AdaLN
         rows (one row broadcast when mod_stride == 0, else one per sample)."""
@@ -317,9 +332,7 @@ class Score(nn.Module):
                      gate_stride=mod_stride, rows_per_gate=T)
             ops.layernorm_mod(ws.h, ws.a, shift=mview(base + 3 * Hd), scale=mview(base + 4 * Hd), mod_stride=mod_stride,
                               rows_per_mod=T)
-            ops.gemm(ws.a, W["w_fc1"], W["b_fc1"], ws.hid, EPI_BIAS_GELU_BF16)
-            ops.gemm(ws.hid, W["w_fc2"], W["b_fc2"], ws.h, EPI_GATE_RESID_F32, resid=ws.h, gate=mview(base + 5 * Hd),
-                     gate_stride=mod_stride, rows_per_gate=T)
+            self._mlp(ws, W, mview(base + 5 * Hd), mod_stride, T)
         base = self.num_blocks * 6 * Hd
         ops.layernorm_mod(ws.h, ws.a, shift=mview(base), scale=mview(base + Hd), mod_stride=mod_stride, rows_per_mod=T)
         ops.gemm(ws.a, P["w_out"], P["b_out"], out, EPI_BIAS_F32, N=self.z_dim)
@@ -350,9 +363,7 @@ class Score(nn.Module):
 
         def mlp_half(W, base_shift, base_scale, base_gate):
             ops.layernorm_mod(ws.h, ws.a, shift=mview(base_shift), scale=mview(base_scale), mod_stride=mod_stride, rows_per_mod=T)
-            ops.gemm(ws.a, W["w_fc1"], W["b_fc1"], ws.hid, EPI_BIAS_GELU_BF16)
-            ops.gemm(ws.hid, W["w_fc2"], W["b_fc2"], ws.h, EPI_GATE_RESID_F32, resid=ws.h, gate=mview(base_gate),
-                     gate_stride=mod_stride, rows_per_gate=T)
+            self._mlp(ws, W, mview(base_gate), mod_stride, T)
 
         ops.cast_pad_bf16(x_tokens, ws.xa.shape[1], out=ws.xa)
         ops.gemm(ws.xa, P["w_in"], P["b_in"], ws.h, EPI_BIAS_F32)

@@ -140,3 +140,40 @@ def test_shard_ranges_cover_exactly():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [e - b for b, e in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("tiles_m,tn1,tn2,kb1,kb2,pairs", [(32, 16, 4, 16, 64, 74), (8, 16, 4, 16, 64, 74), (1, 16, 4, 16, 64, 16),
+                                                           (5, 4, 1, 4, 16, 20), (16, 2, 2, 8, 8, 32), (33, 16, 4, 16, 64, 74),
+                                                           (32, 16, 4, 16, 64, 66), (7, 3, 5, 4, 12, 74)])
+def test_fused_mlp_static_schedule_covers_every_tile_once(tiles_m, tn1, tn2, kb1, kb2, pairs):
+    """Host view of mlp.cu's static work lists (ldt_mlp_schedule_item): every fc1 and fc2 tile appears exactly once, a pair
+    never starts an fc2 tile before its last fc1 tile (the deadlock-freedom argument), and the k-block load is balanced."""
+    import ctypes as C
+    from ldt_b200 import _lib
+    lib = _lib.load()
+    seen1, seen2, loads = set(), set(), []
+    for p in range(pairs):
+        n, ph, mb, nt = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        assert lib.ldt_mlp_schedule_item(tiles_m, tn1, tn2, kb1, kb2, pairs, p, 0, C.byref(n), C.byref(ph), C.byref(mb), C.byref(nt)) == 0
+        in_phase2, load = False, 0
+        for it in range(n.value):
+            lib.ldt_mlp_schedule_item(tiles_m, tn1, tn2, kb1, kb2, pairs, p, it, C.byref(n), C.byref(ph), C.byref(mb), C.byref(nt))
+            if ph.value == 0:
+                assert not in_phase2
+                continue
+            assert 0 <= mb.value < tiles_m
+            if ph.value == 1:
+                assert not in_phase2, "fc1 tile after an fc2 tile"
+                assert 0 <= nt.value < tn1 and (mb.value, nt.value) not in seen1
+                seen1.add((mb.value, nt.value))
+                load += kb1
+            else:
+                in_phase2 = True
+                assert 0 <= nt.value < tn2 and (mb.value, nt.value) not in seen2
+                seen2.add((mb.value, nt.value))
+                load += kb2
+        loads.append(load)
+    assert len(seen1) == tiles_m * tn1 and len(seen2) == tiles_m * tn2
+    ideal = (tiles_m * tn1 * kb1 + tiles_m * tn2 * kb2) / pairs
+    if (tiles_m * tn2) % pairs != 0 and kb2 % kb1 == 0 and tiles_m * tn1 >= 4 * pairs:   # the balanced regime
+        assert max(loads) <= ideal + kb2 / 2 + kb1, (max(loads), ideal)

@@ -275,6 +275,58 @@ def test_gemm_tcgen05_matches_cross_check_bitwise_on_exact_inputs(dev):
             assert torch.equal(o1, ref)
 
 
+@pytest.mark.parametrize("M,Cc,inner", [(8192, 1024, 4096), (2048, 1024, 4096), (1056, 256, 1024), (4096, 512, 512), (1024, 256, 256)])
+def test_fused_mlp_equals_two_gemm_launches_bitwise(dev, M, Cc, inner):
+    """ldt_mlp_bf16 (fc1 + GELU -> fc2 + gate + residual in one persistent kernel, fc2 tiles released per 256-row block
+    by global completion counters) runs the same tile arithmetic as the two ldt_gemm_bf16 launches: bit-identical
+    outputs AND hidden activations; the counters are left zero, so the same buffer serves the next launch."""
+    from ldt_b200 import ops
+    g = torch.Generator().manual_seed(M + Cc + inner)
+    A = (torch.randn((M, Cc), generator=g) * 0.7).to(dev).bfloat16()
+    W1 = (torch.randn((inner, Cc), generator=g) / Cc ** 0.5).to(dev).bfloat16()
+    W2 = (torch.randn((Cc, inner), generator=g) / inner ** 0.5).to(dev).bfloat16()
+    b1 = torch.randn((inner,), generator=g).to(dev)
+    b2 = torch.randn((Cc,), generator=g).to(dev)
+    resid = torch.randn((M, Cc), generator=g).to(dev)
+    rpg = 32
+    gate = torch.randn(((M + rpg - 1) // rpg, Cc), generator=g).to(dev)
+    # the two-launch path
+    hid_ref = torch.empty((M, inner), dtype=torch.bfloat16, device=dev)
+    out_ref = resid.clone()
+    ops.gemm(A, W1, b1, hid_ref, 2, backend=3)
+    ops.gemm(hid_ref, W2, b2, out_ref, 3, resid=out_ref, gate=gate, gate_stride=Cc, rows_per_gate=rpg, backend=3)
+    # against plain torch (same bf16 rounding point for the hidden activations)
+    h32 = torch.nn.functional.gelu(A.float() @ W1.float().t() + b1).bfloat16().float()
+    ref = resid + gate.repeat_interleave(rpg, 0)[:M] * (h32 @ W2.float().t() + b2)
+    assert rel_rms_err(out_ref, ref) < 4e-3
+    sync = ops.mlp_sync_buffer(M, dev)
+    for rep in range(3):   # repeated launches on one counter buffer: the kernel must leave it clean
+        hid = torch.zeros((M, inner), dtype=torch.bfloat16, device=dev)
+        out = resid.clone()
+        ops.mlp(A, W1, b1, hid, W2, b2, out, sync, resid=out, gate=gate, gate_stride=Cc, rows_per_gate=rpg)
+        torch.cuda.synchronize()
+        assert torch.equal(hid, hid_ref), f"hidden activations differ (launch {rep})"
+        assert torch.equal(out, out_ref), f"fused MLP output differs (launch {rep}): max {(out - out_ref).abs().max()}"
+        assert int(sync.abs().sum()) == 0, "completion counters not left clean"
+    # broadcast gate row (unconditional sampling: one AdaLN row for the whole batch) and no gate at all
+    out = resid.clone()
+    ops.mlp(A, W1, b1, hid, W2, b2, out, sync, resid=out, gate=gate[:1], gate_stride=0, rows_per_gate=rpg)
+    o2 = resid.clone()
+    ops.gemm(hid_ref, W2, b2, o2, 3, resid=o2, gate=gate[:1], gate_stride=0, rows_per_gate=rpg, backend=3)
+    assert torch.equal(out, o2)
+
+
+def test_fused_mlp_rejects_unsupported_shapes(dev):
+    from ldt_b200 import ops
+    A = torch.zeros((1024, 128), dtype=torch.bfloat16, device=dev)
+    W1 = torch.zeros((512, 128), dtype=torch.bfloat16, device=dev)
+    W2 = torch.zeros((128, 512), dtype=torch.bfloat16, device=dev)
+    hid = torch.zeros((1024, 512), dtype=torch.bfloat16, device=dev)
+    out = torch.zeros((1024, 128), device=dev)
+    with pytest.raises(RuntimeError, match="multiples of 256"):
+        ops.mlp(A, W1, None, hid, W2, None, out, ops.mlp_sync_buffer(1024, dev))
+
+
 # ------------------------------------------------------------------------------------------------
 # element-wise kernels
 # ------------------------------------------------------------------------------------------------

@@ -35,6 +35,31 @@ def timed(fn, reps=50, warm=5):
     return e0.elapsed_time(e1) / reps
 
 
+def timed_with_clocks(replay, seconds=2.0):
+    """Replay for `seconds`; returns (ms per replay, median SM MHz, mean W) sampled through NVML while it runs."""
+    import threading
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(0)
+    ms1 = timed(replay, reps=20, warm=5)
+    reps = max(20, int(seconds * 1e3 / ms1))
+    samples, stop = [], threading.Event()
+
+    def poll():
+        while not stop.is_set():
+            samples.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), pynvml.nvmlDeviceGetPowerUsage(h) / 1e3))
+            stop.wait(0.02)
+    th = threading.Thread(target=poll)
+    th.start()
+    ms = timed(replay, reps=reps, warm=0)
+    stop.set()
+    th.join()
+    samples = samples[len(samples) // 4:]   # drop the ramp
+    clk = sorted(c for c, _ in samples)[len(samples) // 2] if samples else -1
+    pw = sum(w for _, w in samples) / max(1, len(samples))
+    return ms, clk, pw
+
+
 def graph_of(fn):
     fn()
     torch.cuda.synchronize()
@@ -86,8 +111,71 @@ def main():
                 for name, *_ in SHAPES:
                     f(name, i)
         gr = graph_of(chain)
-        ms = timed(gr.replay, reps=100, warm=20)
-        print(f"chain of 96 GEMMs, graph replay, {tag}: {ms:7.3f} ms  {tot_fl / ms / 1e9:8.1f} TFLOP/s", flush=True)
+        ms, clk, pw = timed_with_clocks(gr.replay)
+        print(f"chain of 96 GEMMs, graph replay, {tag}: {ms:7.3f} ms  {tot_fl / ms / 1e9:8.1f} TFLOP/s  [SM {clk} MHz, {pw:.0f} W]", flush=True)
+
+    # fused MLP kernel against its two launches
+    A1, W1s, b1, _, _, hid, _, _, _ = ops_["fc1"]
+    _, W2s, b2, gate2, out2, _, _, _, _ = ops_["fc2"]
+    sync = ops.mlp_sync_buffer(M, dev)
+    k = [0]
+
+    def two():
+        ours("fc1", k[0] % 24)
+        ours("fc2", k[0] % 24)
+        k[0] += 1
+
+    def fused():
+        i = k[0] % 24
+        ops.mlp(A1, W1s[i], b1, hid, W2s[i], b2, out2, sync, resid=out2, gate=gate2, gate_stride=0, rows_per_gate=32)
+        k[0] += 1
+    fl = tf("fc1", 1.0) + tf("fc2", 1.0)
+    for tag, f, mode in (("fc1 ; fc2 (two launches)", two, 0), ("fused MLP kernel", fused, 0), ("fused MLP, counters ignored", fused, 8)):
+        _lib.load().ldt_debug_set_gemm_mode(mode)
+        ms = timed(f)
+        _lib.load().ldt_debug_set_gemm_mode(0)
+        sync.zero_()
+        print(f"{tag:28s}: {ms * 1e3:8.2f} us {fl / ms:8.1f} TFLOP/s", flush=True)
+
+    def chain_fused():
+        for i in range(24):
+            ours("qkv", i)
+            ours("fc_o", i)
+            ops.mlp(A1, W1s[i], b1, hid, W2s[i], b2, out2, sync, resid=out2, gate=gate2, gate_stride=0, rows_per_gate=32)
+    gr = graph_of(chain_fused)
+    ms, clk, pw = timed_with_clocks(gr.replay)
+    print(f"chain with the fused MLP kernel, graph replay: {ms:7.3f} ms  {tot_fl / ms / 1e9:8.1f} TFLOP/s  [SM {clk} MHz, {pw:.0f} W]", flush=True)
+    for name in ("fc1", "fc2", "qkv", "fc_o"):   # one shape at a time, sustained: clock and power each kernel settles at
+        def one_shape():
+            for i in range(24):
+                ours(name, i)
+        gr = graph_of(one_shape)
+        ms, clk, pw = timed_with_clocks(gr.replay, 1.5)
+        print(f"sustained 24 x {name:5s} ours  : {ms / 24 * 1e3:8.2f} us {tf(name, ms / 24):8.1f} TFLOP/s  [SM {clk} MHz, {pw:.0f} W]", flush=True)
+
+        def one_shape_cublas():
+            for i in range(24):
+                cublas(name, i)
+        gr = graph_of(one_shape_cublas)
+        ms, clk, pw = timed_with_clocks(gr.replay, 1.5)
+        print(f"sustained 24 x {name:5s} cuBLAS: {ms / 24 * 1e3:8.2f} us {tf(name, ms / 24):8.1f} TFLOP/s  [SM {clk} MHz, {pw:.0f} W]", flush=True)
+
+    def mlp_only():
+        for i in range(24):
+            ops.mlp(A1, W1s[i], b1, hid, W2s[i], b2, out2, sync, resid=out2, gate=gate2, gate_stride=0, rows_per_gate=32)
+    gr = graph_of(mlp_only)
+    ms, clk, pw = timed_with_clocks(gr.replay, 1.5)
+    print(f"sustained 24 x fused MLP   : {ms / 24 * 1e3:8.2f} us {fl / (ms / 24):8.1f} TFLOP/s  [SM {clk} MHz, {pw:.0f} W]", flush=True)
+
+    def two_only():
+        for i in range(24):
+            ours("fc1", i)
+            ours("fc2", i)
+    gr = graph_of(two_only)
+    ms, clk, pw = timed_with_clocks(gr.replay, 1.5)
+    print(f"sustained 24 x (fc1 ; fc2) : {ms / 24 * 1e3:8.2f} us {fl / (ms / 24):8.1f} TFLOP/s  [SM {clk} MHz, {pw:.0f} W]", flush=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "none":
+        return
 
     lib = _lib.load()
     print("== CTA-pair kernel with parts removed (timing only)")
