@@ -331,11 +331,11 @@ __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f +
 // The same function for GEMM epilogues, branch-free and with ONE special-function op per element.  The epilogue of the
 // fc1 GEMM is bound by the MUFU pipe (16 lanes/clk/SM: a warp-wide MUFU occupies its scheduler's share for 8 cycles), so
 // the form matters more than the FP32 count:
-//     gelu(x) = max(x, 0) - |x/2| * erfc(|x| / sqrt(2)),      erfc(|x| / sqrt(2)) = 2^q(|x|),
+//     gelu(x) = max(x, 0) - |x| * erfc(|x| / sqrt(2)) / 2,      erfc(|x| / sqrt(2)) / 2 = 2^(q(|x|) - 1),
 // q = degree-7 fit of log2(erfc(a / sqrt(2))) on a in [0, 5.6] (weighted for absolute error of erfc); beyond 5.6 erfc
 // < 2.2e-8 and the argument is clamped.  fp32 Horner + ex2.approx: |abs error| <= 3.7e-7, relative error <= 3.1e-5
 // wherever |gelu| > 1e-3 (the Abramowitz-Stegun 7.1.26 form it replaces: 2.1e-7 / 1.7e-4, with rcp + ex2) -- two orders
-// below the bf16 rounding applied to the result.  1 MUFU + 11 FP32-pipe ops.
+// below the bf16 rounding applied to the result.  1 MUFU + 10 FP32-pipe ops.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
 #ifdef LDT_GELU_AS   // A/B builds only: the Abramowitz-Stegun 7.1.26 form (rcp + ex2) this replaced
   float t, e;
@@ -356,11 +356,43 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   q = fmaf(q, a, -5.273329248e-02f);
   q = fmaf(q, a, -4.591345845e-01f);
   q = fmaf(q, a, -1.151114419e+00f);
-  q = fmaf(q, a, 3.068670393e-07f);
+  q = fmaf(q, a, 3.068670393e-07f - 1.0f);   // -1: the factor 1/2 of |x/2| rides in the exponent
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
-  return fmaf(-fabsf(0.5f * x), e, fmaxf(x, 0.0f));
+  return fmaf(-fabsf(x), e, fmaxf(x, 0.0f));
 #endif
+}
+// Two elements at a time with Blackwell's packed fp32 arithmetic (FFMA2: one issue slot for two FMAs): the degree-7 Horner
+// chain, which is 7 of the 11 FP32 ops of gelu_erf_fast, issues half as many instructions.  Same arithmetic per element
+// (fma.rn.f32x2 rounds each half like fma.rn.f32), so the results are bit-identical to gelu_erf_fast.
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ void gelu_erf_fast_x2(float& x0, float& x1) {
+  const uint64_t a = pack_f32x2(fminf(fabsf(x0), 5.6f), fminf(fabsf(x1), 5.6f));
+  uint64_t q = fma_f32x2(pack_f32x2(7.732903964e-06f, 7.732903964e-06f), a, pack_f32x2(-4.679716980e-05f, -4.679716980e-05f));
+  q = fma_f32x2(q, a, pack_f32x2(-4.473918779e-04f, -4.473918779e-04f));
+  q = fma_f32x2(q, a, pack_f32x2(7.435896264e-03f, 7.435896264e-03f));
+  q = fma_f32x2(q, a, pack_f32x2(-5.273329248e-02f, -5.273329248e-02f));
+  q = fma_f32x2(q, a, pack_f32x2(-4.591345845e-01f, -4.591345845e-01f));
+  q = fma_f32x2(q, a, pack_f32x2(-1.151114419e+00f, -1.151114419e+00f));
+  q = fma_f32x2(q, a, pack_f32x2(3.068670393e-07f - 1.0f, 3.068670393e-07f - 1.0f));
+  float q0, q1, e0, e1;
+  unpack_f32x2(q, q0, q1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1));
+  x0 = fmaf(-fabsf(x0), e0, fmaxf(x0, 0.0f));
+  x1 = fmaf(-fabsf(x1), e1, fmaxf(x1, 0.0f));
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);

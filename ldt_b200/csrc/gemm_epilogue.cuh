@@ -251,8 +251,13 @@ __device__ __forceinline__ void epilogue_staged(const EpiParams& p, uint8_t* stg
           f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
         }
         if constexpr (EPI == LDT_EPI_BIAS_GELU_BF16 && !(XM & 64)) {
+#ifdef LDT_GELU_SCALAR   // A/B builds only
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = gelu_erf_fast(f[j]);
+#else
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) gelu_erf_fast_x2(f[j], f[j + 1]);
+#endif
         }
         const uint32_t a = st_row + static_cast<uint32_t>((c ^ (lane & 7)) << 4);
         if constexpr (!(XM & 16)) {

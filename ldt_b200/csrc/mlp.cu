@@ -111,8 +111,8 @@ __device__ __forceinline__ void wait_counter_ge(const unsigned int* ctr, unsigne
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 mlp_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
-               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2, const MlpParams p,
-               const MlpSched S) {
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2,
+               const __grid_constant__ CUtensorMap tmH, const MlpParams p, const MlpSched S) {
   using Cfg = Tc2Cfg<MLP_BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -253,9 +253,16 @@ mlp_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     // deferred to the moment the NEXT fc1 tile's accumulator is ready (the stores drained long ago), and done at once
     // only when the next item is an fc2 tile, which may itself depend on the slab.
     int pending_mb = -1;
+    const CUtensorMap* tm_hid = p.e1.tma_store ? &tmH : nullptr;   // hidden activations leave through bulk tensor stores
     auto publish = [&]() {
       if (pending_mb >= 0 && !p.nosync) {
-        if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.sync + pending_mb) : "memory");
+        if (lane == 0) {
+          if (tm_hid != nullptr) {
+            tma_store_wait_all();          // the slab's bulk stores (async proxy, issued by this lane) are performed ...
+            fence_proxy_async_global();    // ... and ordered before the generic-proxy release below
+          }
+          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.sync + pending_mb) : "memory");
+        }
       }
       pending_mb = -1;
     };
@@ -271,7 +278,7 @@ mlp_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           mbar_wait(&tfull[acc], acc_phase);
           tc_fence_after();
           publish();   // the previous fc1 tile's slab
-        });
+        }, tm_hid);
       } else {
         publish();     // before blocking on an accumulator that may need this very slab
         epilogue_staged<LDT_EPI_GATE_RESID_F32, MLP_BN / 2>(p.e2, stg, lane, m0 + quad * 32, col, taddr, [&]() {
@@ -291,6 +298,7 @@ mlp_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       if (acc == 0) acc_phase ^= 1u;
     }
     publish();
+    if (tm_hid != nullptr && lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   cluster_sync_all();
@@ -350,7 +358,7 @@ extern "C" int ldt_mlp_bf16(const ldt_mlp_args* args, void* stream) {
   const int P = min(min(num_sms() / 2, max_pairs), tiles_m * tn1);
   const MlpSched S = mlp_make_sched(tiles_m, tn1, tn2, a.C / TC_BK, a.inner / TC_BK, P);
 
-  CUtensorMap tmA1, tmW1, tmA2, tmW2;
+  CUtensorMap tmA1, tmW1, tmA2, tmW2, tmH;
   int rc = make_tmap_bf16(&tmA1, a.A, a.M, a.C, a.lda, 128);
   if (rc) return rc;
   rc = make_tmap_bf16(&tmW1, a.W1, a.inner, a.C, a.ldw1, MLP_BN / 2);
@@ -359,10 +367,12 @@ extern "C" int ldt_mlp_bf16(const ldt_mlp_args* args, void* stream) {
   if (rc) return rc;
   rc = make_tmap_bf16(&tmW2, a.W2, a.C, a.inner, a.ldw2, MLP_BN / 2);
   if (rc) return rc;
+  rc = make_tmap_bf16(&tmH, a.hidden, a.M, a.inner, a.ldh, 32);   // store boxes of the fc1 epilogue
+  if (rc) return rc;
 
   MlpParams p;
   p.e1.M = a.M; p.e1.N = a.inner; p.e1.bias = a.bias1; p.e1.out = a.hidden; p.e1.ldo = a.ldh;
-  p.e1.resid = nullptr; p.e1.gate = nullptr; p.e1.gate_stride = 0; p.e1.rows_per_gate = 1; p.e1.dbg = nullptr; p.e1.dbg_mode = 0; p.e1.tma_store = 0;
+  p.e1.resid = nullptr; p.e1.gate = nullptr; p.e1.gate_stride = 0; p.e1.rows_per_gate = 1; p.e1.dbg = nullptr; p.e1.dbg_mode = 0; p.e1.tma_store = (ldt_debug_get_gemm_mode() & 256) ? 0 : 1;
   p.e2.M = a.M; p.e2.N = a.C; p.e2.bias = a.bias2; p.e2.out = a.out; p.e2.ldo = a.ldo;
   p.e2.resid = a.resid; p.e2.gate = a.gate; p.e2.gate_stride = a.gate_stride;
   p.e2.rows_per_gate = a.rows_per_gate > 0 ? a.rows_per_gate : 1; p.e2.dbg = nullptr; p.e2.dbg_mode = 0; p.e2.tma_store = 0;
@@ -372,7 +382,7 @@ extern "C" int ldt_mlp_bf16(const ldt_mlp_args* args, void* stream) {
   p.tiles_m = tiles_m;
   p.nosync = (ldt_debug_get_gemm_mode() & 8) ? 1 : 0;
   if (p.nosync) p.ready_target = 0;
-  LDT_CUDA_OK(launch_pdl(mlp_tc2_kernel, dim3(2 * P), dim3(TC_THREADS), Cfg::SMEM_BYTES, s, tmA1, tmW1, tmA2, tmW2, p, S));
+  LDT_CUDA_OK(launch_pdl(mlp_tc2_kernel, dim3(2 * P), dim3(TC_THREADS), Cfg::SMEM_BYTES, s, tmA1, tmW1, tmA2, tmW2, tmH, p, S));
   return LDT_OK;
 }
 

@@ -179,8 +179,10 @@ class Score(nn.Module):
         # unfused GEMM + attention kernels (kept for cross-attention blocks and as a cross-check in the tests)
         self.fused_attention = True
         # the MLP half of a block (fc1 + GELU -> fc2 + gate + residual) runs as ONE persistent kernel when the shapes fill
-        # whole CTA-pair tiles (ops.mlp_supported); False selects the two GEMM launches (bit-identical, kept as cross-check)
-        self.fused_mlp = True
+        # whole CTA-pair tiles (ops.mlp_supported).  Bit-identical to the two GEMM launches and 17 % faster than them at
+        # boost clocks, but at the board's power cap the whole token pass measures the same (5.34 vs 5.31 ms, interleaved
+        # A/B, tools/exp_step_ab.py): the default stays with the two launches, which wait on nothing.
+        self.fused_mlp = False
 
     # ------------------------------------------------------------------------------------------
     # weight packing (fp32 parameters -> bf16 K-major GEMM operands), invalidated when any parameter's

@@ -130,6 +130,13 @@ def test_score_full_width_few_blocks_vs_emulating_oracle(dev, blocks, batch):
     emu = emulated(lambda: O.score_forward(sd, cfg, x, t))
     assert rms_rel_err(out, emu) < TOL_RMS_EMUL, rms_rel_err(out, emu)
     check_vs_fp32(out, O.score_forward(sd, cfg, x, t))
+    if batch * 32 >= 1024:
+        # the one-launch MLP kernel (opt-in) runs the same tile arithmetic as the two GEMM launches: same bits
+        model.fused_mlp = True
+        with torch.no_grad():
+            fused = model(x.to(dev), t.to(dev))
+        model.fused_mlp = False
+        assert torch.equal(fused, out)
 
 
 def test_score_vs_oracle_float64_on_ragged_batch(dev):

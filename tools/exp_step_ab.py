@@ -30,7 +30,10 @@ def main():
     mod = torch.randn((1, ws.mod_len), device=dev) * 0.1
     graphs = []
     for v in vals:
-        if key.startswith("env:"):
+        if key == "pdl":   # programmatic dependent launch on / off (ldt_set_pdl), read at capture time
+            from ldt_b200 import _lib
+            _lib.load().ldt_set_pdl(int(v))
+        elif key.startswith("env:"):
             os.environ[key[4:]] = v
         else:
             setattr(model, key, type(getattr(model, key))(int(v)))
