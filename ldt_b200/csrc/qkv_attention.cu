@@ -209,6 +209,7 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[set]), 0));
 
+#ifndef LDT_QA_SKIP_ATTN   // A/B builds only (tools/exp_ab_lib.py): how much of the kernel is the attention arithmetic
       // ---- S = Q K^T (32 x 32), fragments from the staged tile ----
       float s[2][4][4];
 #pragma unroll
@@ -332,6 +333,10 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 pack_bf16(acc[mi][nn][2] * inv_sum[mi][1], acc[mi][nn][3] * inv_sum[mi][1]);
           }
       }
+#else
+      __nv_bfloat16* so = stg + 32 * QA_V_LD;
+      (void)vv0; (void)vv1; (void)g; (void)t;
+#endif
       __syncwarp();
       if (live) {
         const int b = row0 >> 5;

@@ -32,6 +32,28 @@ def main():
     libs = {"product": _lib.load(), tag: load_variant(tag)}
     g = torch.Generator().manual_seed(0)
     for name in names:
+        if name == "attn":   # the fused projection + attention kernel
+            A = torch.randn((M, 1024), generator=g).to(dev).bfloat16()
+            Wp = [(torch.randn((3072, 1024), generator=g) / 32).to(dev).bfloat16() for _ in range(24)]
+            bp = torch.randn((3072,), generator=g).to(dev)
+            o = torch.empty((M, 1024), dtype=torch.bfloat16, device=dev)
+            graphs = {}
+            for k, lib in libs.items():
+                _lib._lib = lib
+
+                def body():
+                    for i in range(24):
+                        ops.qkv_attention(M // 32, 16, A, Wp[i], bp, o)
+                graphs[k] = graph_of(body)
+            _lib._lib = libs["product"]
+            tot = {k: 0.0 for k in libs}
+            for r in range(3):
+                for k in libs:
+                    ms, clk, pw = timed_with_clocks(graphs[k].replay, 0.8)
+                    tot[k] += ms / 3
+            for k in libs:
+                print(f"attn  {k:8s}: {tot[k] / 24 * 1e3:8.2f} us (sustained, interleaved x3)", flush=True)
+            continue
         N, K, epi = SH[name]
         A = (torch.randn((M, K), generator=g) * 0.5).to(dev).bfloat16()
         W = [(torch.randn((N, K), generator=g) / K ** 0.5).to(dev).bfloat16() for _ in range(24)]
