@@ -20,6 +20,23 @@ __device__ __forceinline__ float sqdist_ref(float dx, float dy, float dz) {
   return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
+// The same distance for TWO queries against one candidate with Blackwell's packed fp32 arithmetic (FADD2 / FMUL2 / FFMA2:
+// one issue slot, two results).  add/mul/fma.rn.f32x2 round each half exactly like their scalar forms, so both halves are
+// bit-identical to sqdist_ref.
+__device__ __forceinline__ uint64_t sub_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t sqdist_ref_x2(uint64_t dx, uint64_t dy, uint64_t dz) {
+  return fma_f32x2(dz, dz, fma_f32x2(dx, dx, mul_f32x2(dy, dy)));
+}
+
 // ------------------------------------------------------------------------------------------------
 // Kernel 1: one direction with argmin (drop-in for NmDistanceKernel).  grid = (query tiles, batch).
 // Each thread owns QPT query points in registers; candidates stream through shared memory as
@@ -94,6 +111,9 @@ __global__ void __launch_bounds__(NN_THREADS) nn_argmin_kernel(int n, const floa
 // (registers) and the per-candidate minimum (warp REDUX.MIN on the float bit pattern -- distances are
 // non-negative so unsigned order == float order -- then one shared-memory atomicMin per warp).
 // No indices are produced: _pairwise_CD_ discards them (evaluation_metrics.py:190-191).
+// The six FP32 operations of a distance run packed, two queries per instruction (candidates sit in shared memory with
+// every coordinate duplicated, (x,x,y,y) + (z,z), so a broadcast load IS the packed operand): 3 issue slots per point
+// pair for the distance + 1 for the two 3-input minima, where the scalar form needed 6 + 1.
 // ------------------------------------------------------------------------------------------------
 constexpr int CD_THREADS = 256;
 constexpr int CD_QPT = 8;                         // query points per thread
@@ -106,8 +126,9 @@ __global__ void __launch_bounds__(CD_THREADS) pairwise_cd_kernel(int nb, int pa,
                                                                 float* __restrict__ out) {
   extern __shared__ float4 cd_smem[];
   const int pb32 = (pb + 31) & ~31;                              // candidates padded to whole groups of 32
-  float4* cand = cd_smem;                                        // [pb32]
-  unsigned* colmin = reinterpret_cast<unsigned*>(cand + pb32);   // [pb32]
+  float4* cand_xy = cd_smem;                                     // [pb32] (x, x, y, y)
+  float2* cand_z = reinterpret_cast<float2*>(cand_xy + pb32);    // [pb32] (z, z)
+  unsigned* colmin = reinterpret_cast<unsigned*>(cand_z + pb32); // [pb32]
   __shared__ double red[2][CD_THREADS / 32];
 
   const int i = row_begin + blockIdx.y;
@@ -119,7 +140,9 @@ __global__ void __launch_bounds__(CD_THREADS) pairwise_cd_kernel(int nb, int pa,
   const float inf = __int_as_float(0x7f800000);
   for (int k = threadIdx.x; k < pb32; k += CD_THREADS) {
     // padding candidates sit at +inf: their distance to anything is +inf, so they never win a minimum
-    cand[k] = (k < pb) ? make_float4(b[k * 3 + 0], b[k * 3 + 1], b[k * 3 + 2], 0.f) : make_float4(inf, inf, inf, 0.f);
+    const float cx = (k < pb) ? b[k * 3 + 0] : inf, cy = (k < pb) ? b[k * 3 + 1] : inf, cz = (k < pb) ? b[k * 3 + 2] : inf;
+    cand_xy[k] = make_float4(cx, cx, cy, cy);
+    cand_z[k] = make_float2(cz, cz);
     colmin[k] = 0x7f800000u;  // +inf
   }
   __syncthreads();
@@ -139,6 +162,13 @@ __global__ void __launch_bounds__(CD_THREADS) pairwise_cd_kernel(int nb, int pa,
       qz[u] = a[pc * 3 + 2];
       best[u] = inf;
     }
+    uint64_t qx2[CD_QPT / 2], qy2[CD_QPT / 2], qz2[CD_QPT / 2];   // queries (u, u+1) packed
+#pragma unroll
+    for (int u = 0; u < CD_QPT; u += 2) {
+      qx2[u / 2] = pack_f32x2(qx[u], qx[u + 1]);
+      qy2[u / 2] = pack_f32x2(qy[u], qy[u + 1]);
+      qz2[u / 2] = pack_f32x2(qz[u], qz[u + 1]);
+    }
     // Candidates go two at a time so that every running minimum is a 3-input FMNMX3 (min of the old value and two
     // new distances): 0.5 min instructions per point pair for the row minima and 0.5 for the column minima, on top of
     // the 6 FP32 operations of the distance itself.  The warp-wide column minimum (REDUX) of candidate k0+j is parked
@@ -148,15 +178,16 @@ __global__ void __launch_bounds__(CD_THREADS) pairwise_cd_kernel(int nb, int pa,
       unsigned mycol = 0x7f800000u;
 #pragma unroll
       for (int jj = 0; jj < 32; jj += 2) {
-        const float4 p0 = cand[k0 + jj];
-        const float4 p1 = cand[k0 + jj + 1];
+        const float4 a0 = cand_xy[k0 + jj], a1 = cand_xy[k0 + jj + 1];
+        const float2 b0 = cand_z[k0 + jj], b1 = cand_z[k0 + jj + 1];
+        const uint64_t p0x = pack_f32x2(a0.x, a0.y), p0y = pack_f32x2(a0.z, a0.w), p0z = pack_f32x2(b0.x, b0.y);
+        const uint64_t p1x = pack_f32x2(a1.x, a1.y), p1y = pack_f32x2(a1.z, a1.w), p1z = pack_f32x2(b1.x, b1.y);
         float cm0 = inf, cm1 = inf;
 #pragma unroll
         for (int u = 0; u < CD_QPT; u += 2) {
-          const float d00 = sqdist_ref(p0.x - qx[u], p0.y - qy[u], p0.z - qz[u]);
-          const float d01 = sqdist_ref(p0.x - qx[u + 1], p0.y - qy[u + 1], p0.z - qz[u + 1]);
-          const float d10 = sqdist_ref(p1.x - qx[u], p1.y - qy[u], p1.z - qz[u]);
-          const float d11 = sqdist_ref(p1.x - qx[u + 1], p1.y - qy[u + 1], p1.z - qz[u + 1]);
+          float d00, d01, d10, d11;
+          unpack_f32x2(sqdist_ref_x2(sub_f32x2(p0x, qx2[u / 2]), sub_f32x2(p0y, qy2[u / 2]), sub_f32x2(p0z, qz2[u / 2])), d00, d01);
+          unpack_f32x2(sqdist_ref_x2(sub_f32x2(p1x, qx2[u / 2]), sub_f32x2(p1y, qy2[u / 2]), sub_f32x2(p1z, qz2[u / 2])), d10, d11);
           best[u] = fminf(fminf(best[u], d00), d10);
           best[u + 1] = fminf(fminf(best[u + 1], d01), d11);
           cm0 = fminf(fminf(cm0, d00), d01);
@@ -233,7 +264,7 @@ extern "C" int ldt_pairwise_cd(int na, int nb, int pa, int pb, const float* a, c
   const int rows = row_end - row_begin;
   if (rows == 0 || nb == 0) return LDT_OK;
   LDT_REQUIRE(a && b && out, LDT_ERR_INVALID, "ldt_pairwise_cd: null pointer");
-  const size_t smem = static_cast<size_t>((pb + 31) & ~31) * (sizeof(float4) + sizeof(unsigned));
+  const size_t smem = static_cast<size_t>((pb + 31) & ~31) * (sizeof(float4) + sizeof(float2) + sizeof(unsigned));
   LDT_REQUIRE(smem <= 200 * 1024, LDT_ERR_UNSUPPORTED, "ldt_pairwise_cd: pb=%d needs %zu B of shared memory", pb, smem);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   static bool attr_set = false;
