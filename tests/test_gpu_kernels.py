@@ -275,6 +275,27 @@ def test_gemm_tcgen05_matches_cross_check_bitwise_on_exact_inputs(dev):
             assert torch.equal(o1, ref)
 
 
+@pytest.mark.parametrize("M,N,K", [(512, 256, 64), (768, 256, 256), (2304, 1024, 4096), (8192, 1024, 1024), (1000, 512, 512)])
+def test_gemm_cluster4_multicast_equals_pair_kernel_bitwise(dev, M, N, K):
+    """backend 4 = clusters of two CTA pairs sharing the W tile by TMA multicast (gemm_tc4_kernel): same tile arithmetic
+    as the pair kernel, so every epilogue must give the same bits, including a ragged / odd number of 256-row tiles."""
+    from ldt_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn((M, K), generator=g) * 0.5).to(dev).bfloat16()
+    W = (torch.randn((N, K), generator=g) / K ** 0.5).to(dev).bfloat16()
+    bias = torch.randn((N,), generator=g).to(dev)
+    resid = torch.randn((M, N), generator=g).to(dev)
+    gate = torch.randn(((M + 31) // 32, N), generator=g).to(dev)
+    for epi, dt in ((0, torch.float32), (1, torch.bfloat16), (2, torch.bfloat16), (3, torch.float32)):
+        outs = []
+        for backend in (3, 4):
+            out = resid.clone() if epi == 3 else torch.full((M, N), 7.0, dtype=dt, device=dev)
+            kw = dict(resid=out, gate=gate, gate_stride=N, rows_per_gate=32) if epi == 3 else {}
+            ops.gemm(A, W, bias, out, epi, backend=backend, **kw)
+            outs.append(out)
+        assert torch.equal(outs[0], outs[1]), f"epilogue {epi}: max diff {(outs[0].float() - outs[1].float()).abs().max()}"
+
+
 @pytest.mark.parametrize("M,Cc,inner", [(8192, 1024, 4096), (2048, 1024, 4096), (1056, 256, 1024), (4096, 512, 512), (1024, 256, 256)])
 def test_fused_mlp_equals_two_gemm_launches_bitwise(dev, M, Cc, inner):
     """ldt_mlp_bf16 (fc1 + GELU -> fc2 + gate + residual in one persistent kernel, fc2 tiles released per 256-row block
