@@ -653,7 +653,11 @@ static int launch_tc2(const ldt_gemm_args& a, const EpiParams& p, cudaStream_t s
   }
   const int tiles_m = (a.M + T2_BM - 1) / T2_BM;
   const int tiles_n = (a.N + BN - 1) / BN;
-  const int pairs = min(tiles_m * tiles_n, num_sms() / 2);
+  // Only as many CTA pairs as the wave count needs: 128 tiles are two waves on 64 pairs exactly as on 74, and at the board's
+  // power cap the ten pairs that would idle through the second wave are clock for the others.
+  const int tiles = tiles_m * tiles_n, max_pairs = num_sms() / 2;
+  const int waves = (tiles + max_pairs - 1) / max_pairs;
+  const int pairs = (p.dbg_mode & 512) ? min(tiles, max_pairs) : (tiles + waves - 1) / waves;
   CUtensorMap tmO = tmA;   // only read by the bf16-output epilogues
   if (p.tma_store && (EPI == LDT_EPI_BIAS_BF16 || EPI == LDT_EPI_BIAS_GELU_BF16)) {
     rc = make_tmap_bf16(&tmO, a.out, a.M, a.N, a.ldo, 32);   // store boxes: 32 rows x 64 columns, 128-byte swizzle
