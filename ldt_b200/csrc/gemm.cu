@@ -14,6 +14,7 @@
 // 172,238; model/scorenet/score.py:95; model/Compressor/Network.py:61,153), which the reference runs as
 // separate cuDNN/cuBLAS launches followed by separate element-wise kernels.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
@@ -718,8 +719,16 @@ static int launch_any(const ldt_gemm_args& a, const EpiParams& p, cudaStream_t s
     LDT_REQUIRE(a.N % 256 == 0, LDT_ERR_UNSUPPORTED, "ldt_gemm_bf16: backend 4 needs N %% 256 == 0 (N=%d)", a.N);
     return launch_tc4<256, EPI>(a, p, s);
   }
-  // backend 0 picks: CTA pairs (256-row tiles) once there are enough rows to fill them, else single-CTA tiles.
-  const bool pair_ok = (a.backend == 3) || (a.backend == 0 && a.M >= 1024);
+  // backend 0 picks: CTA pairs (256-row tiles) once there is a full tile of rows, else single-CTA tiles.
+  static int pair_min_m = -1;
+  if (pair_min_m < 0) {
+    // smallest M that goes to the CTA-pair kernel.  One full 256-row tile is enough: at M = 512 (batch 16, BASELINE
+    // configs[0]) a token pass takes 1.31 ms on the pair kernel against 2.27 ms on single-CTA tiles, whose epilogue stores
+    // are not staged (1.70 vs 2.27 ms at M = 256).  LDT_PAIR_MIN_M overrides it for experiments.
+    const char* e = getenv("LDT_PAIR_MIN_M");
+    pair_min_m = e ? atoi(e) : 256;
+  }
+  const bool pair_ok = (a.backend == 3) || (a.backend == 0 && a.M >= pair_min_m);
   if (pair_ok && a.backend != 2) {
     if (a.N % 256 == 0) {
       // 256-wide tiles unless they leave most of the machine idle: at M = 2048 (64 clouds per GPU, the completion
