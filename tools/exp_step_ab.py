@@ -30,7 +30,10 @@ def main():
     mod = torch.randn((1, ws.mod_len), device=dev) * 0.1
     graphs = []
     for v in vals:
-        if key == "pdl":   # programmatic dependent launch on / off (ldt_set_pdl), read at capture time
+        if key == "gemm_mode":   # ldt_debug_set_gemm_mode value, read at capture time
+            from ldt_b200 import _lib
+            _lib.load().ldt_debug_set_gemm_mode(int(v))
+        elif key == "pdl":   # programmatic dependent launch on / off (ldt_set_pdl), read at capture time
             from ldt_b200 import _lib
             _lib.load().ldt_set_pdl(int(v))
         elif key.startswith("env:"):
