@@ -36,9 +36,12 @@ def main():
             def body():
                 for i in range(24):
                     ops.gemm(A, W[i], bias, out, epi, backend=3, **kw)
-            if epi != 3:
+            if epi == 3:
+                out.copy_(torch.arange(M * N, device=dev, dtype=torch.float32).view(M, N) * 1e-6)
+                ops.gemm(A, W[0], bias, out, epi, backend=3, **kw)
+            else:
                 ops.gemm(A, W[0], bias, out, epi, backend=3)
-                outs[m] = out.clone()
+            outs[m] = out.clone()
             graphs[m] = graph_of(body)
         lib.ldt_debug_set_gemm_mode(0)
         if len(outs) > 1:
