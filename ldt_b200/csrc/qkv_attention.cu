@@ -388,7 +388,10 @@ extern "C" int ldt_qkv_attention_bf16(int B, int H, int K, const void* A, int ld
   p.M = M; p.H = H; p.bias = bias_p; p.out = static_cast<__nv_bfloat16*>(out);
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(QA_DH));
   const int tiles_m = (M + 255) / 256;
-  const int pairs = min(tiles_m * H, num_sms() / 2);
+  // only as many CTA pairs as the wave count needs (see launch_tc2 in gemm.cu)
+  const int tiles = tiles_m * H, max_pairs = num_sms() / 2;
+  const int waves = (tiles + max_pairs - 1) / max_pairs;
+  const int pairs = (tiles + waves - 1) / waves;
   LDT_CUDA_OK(launch_pdl(qkv_attention_kernel, dim3(2 * pairs), dim3(QA_THREADS), QA_SMEM_BYTES, static_cast<cudaStream_t>(stream),
                          tmA, tmW, p, K, tiles_m));
   return LDT_OK;
