@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(NN_THREADS) nn_argmin_kernel(int n, const floa
                                                              const float* __restrict__ xyz2,
                                                              float* __restrict__ result,
                                                              int* __restrict__ result_i) {
-  __shared__ float4 cand[NN_TILE];
+  __shared__ float4 cand_xy[NN_TILE];   // (x, x, y, y): a broadcast load is the packed operand of both queries
+  __shared__ float2 cand_z[NN_TILE];    // (z, z)
   const int b = blockIdx.y;
   const float* q = xyz + static_cast<size_t>(b) * n * 3;
   const float* c = xyz2 + static_cast<size_t>(b) * m * 3;
@@ -68,29 +69,38 @@ __global__ void __launch_bounds__(NN_THREADS) nn_argmin_kernel(int n, const floa
     best[u] = 0.f;
     best_i[u] = 0;
   }
+  static_assert(NN_QPT == 2, "the two queries of a thread form one packed operand");
+  const uint64_t qx2 = pack_f32x2(qx[0], qx[1]), qy2 = pack_f32x2(qy[0], qy[1]), qz2 = pack_f32x2(qz[0], qz[1]);
   for (int k2 = 0; k2 < m; k2 += NN_TILE) {
     const int cnt = min(NN_TILE, m - k2);
     __syncthreads();
     for (int k = threadIdx.x; k < cnt; k += NN_THREADS) {
       const float* p = c + static_cast<size_t>(k2 + k) * 3;
-      cand[k] = make_float4(p[0], p[1], p[2], 0.f);
+      cand_xy[k] = make_float4(p[0], p[0], p[1], p[1]);
+      cand_z[k] = make_float2(p[2], p[2]);
     }
     __syncthreads();
     if (k2 == 0) {  // candidate 0 initialises the running minimum (reference: `k==0 || d<best`)
-      const float4 p = cand[0];
+      const float4 p = cand_xy[0];
+      const float pz = cand_z[0].x;
 #pragma unroll
-      for (int u = 0; u < NN_QPT; ++u) best[u] = sqdist_ref(p.x - qx[u], p.y - qy[u], p.z - qz[u]);
+      for (int u = 0; u < NN_QPT; ++u) best[u] = sqdist_ref(p.x - qx[u], p.z - qy[u], pz - qz[u]);
     }
 #pragma unroll 4
     for (int k = 0; k < cnt; ++k) {
-      const float4 p = cand[k];
-#pragma unroll
-      for (int u = 0; u < NN_QPT; ++u) {
-        const float d = sqdist_ref(p.x - qx[u], p.y - qy[u], p.z - qz[u]);
-        if (d < best[u]) {
-          best[u] = d;
-          best_i[u] = k2 + k;
-        }
+      // both queries against candidate k in one packed evaluation (each half rounds like sqdist_ref: bit-identical)
+      const float4 a = cand_xy[k];
+      const float2 z = cand_z[k];
+      float d0, d1;
+      unpack_f32x2(sqdist_ref_x2(sub_f32x2(pack_f32x2(a.x, a.y), qx2), sub_f32x2(pack_f32x2(a.z, a.w), qy2),
+                                 sub_f32x2(pack_f32x2(z.x, z.y), qz2)), d0, d1);
+      if (d0 < best[0]) {
+        best[0] = d0;
+        best_i[0] = k2 + k;
+      }
+      if (d1 < best[1]) {
+        best[1] = d1;
+        best_i[1] = k2 + k;
       }
     }
   }
