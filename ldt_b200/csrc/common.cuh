@@ -378,6 +378,11 @@ __device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ void gelu_erf_fast_x2(float& x0, float& x1) {
   const uint64_t a = pack_f32x2(fminf(fabsf(x0), 5.6f), fminf(fabsf(x1), 5.6f));
   uint64_t q = fma_f32x2(pack_f32x2(7.732903964e-06f, 7.732903964e-06f), a, pack_f32x2(-4.679716980e-05f, -4.679716980e-05f));

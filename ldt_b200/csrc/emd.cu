@@ -180,11 +180,6 @@ approx_match_kernel(int n, int m, const float* __restrict__ xyz1, const float* _
 // product of constants formed once per level; sqrt in the cost as sqrt.approx -- both inside the 2e-5 agreement the
 // tests demand against the reference's own kernels.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
 __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));

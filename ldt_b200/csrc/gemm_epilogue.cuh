@@ -202,6 +202,7 @@ __device__ __forceinline__ void epilogue_staged(const EpiParams& p, uint8_t* stg
             const uint32_t a = stg_u32 + static_cast<uint32_t>(rr * 128 + ((cc ^ (rr & 7)) << 4));
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w) : "r"(a));
             if (row < p.M) {
+#ifdef LDT_EPI_SCALAR_F32   // A/B builds only
               a4.x += b4.x; a4.y += b4.y; a4.z += b4.z; a4.w += b4.w;
               if constexpr (EPI == LDT_EPI_GATE_RESID_F32) {
                 float4 g = g4;
@@ -212,6 +213,22 @@ __device__ __forceinline__ void epilogue_staged(const EpiParams& p, uint8_t* stg
                 a4.x = r.x + g.x * a4.x; a4.y = r.y + g.y * a4.y;
                 a4.z = r.z + g.z * a4.z; a4.w = r.w + g.w * a4.w;
               }
+#else
+              // packed fp32 (FADD2 / FFMA2), two columns per instruction; each half rounds like the scalar form
+              uint64_t lo = add_f32x2(pack_f32x2(a4.x, a4.y), pack_f32x2(b4.x, b4.y));
+              uint64_t hi = add_f32x2(pack_f32x2(a4.z, a4.w), pack_f32x2(b4.z, b4.w));
+              if constexpr (EPI == LDT_EPI_GATE_RESID_F32) {
+                float4 g = g4;
+                if (p.gate != nullptr && !gate_uniform)
+                  g = __ldg(reinterpret_cast<const float4*>(
+                      p.gate + static_cast<long long>(row / p.rows_per_gate) * p.gate_stride + col));
+                const float4 r = r4[u & 1][i];
+                lo = fma_f32x2(pack_f32x2(g.x, g.y), lo, pack_f32x2(r.x, r.y));
+                hi = fma_f32x2(pack_f32x2(g.z, g.w), hi, pack_f32x2(r.z, r.w));
+              }
+              unpack_f32x2(lo, a4.x, a4.y);
+              unpack_f32x2(hi, a4.z, a4.w);
+#endif
               *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col) = a4;
             }
           }
