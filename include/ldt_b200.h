@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define LDT_ABI_VERSION 1
+#define LDT_ABI_VERSION 2   /* 2: ldt_sde_step takes rng_state; ldt_pairwise_cd_upper added */
 
 #define LDT_OK 0
 #define LDT_ERR_INVALID (-1)
@@ -54,6 +54,14 @@ int ldt_nn_distance(int b, int n, const float* xyz1, int m, const float* xyz2, f
  *   a [na,pa,3] f32, b [nb,pb,3] f32 -> out [(row_end-row_begin), nb] f32 (row-major). */
 int ldt_pairwise_cd(int na, int nb, int pa, int pb, const float* a, const float* b, int row_begin, int row_end,
                     float* out, void* stream);
+
+/* The same matrix for ONE cloud set against itself (M_rr / M_ss of compute_CD_metrics, evaluation/evaluation_metrics.py:
+ * 311-312, which the reference evaluates in full): only entries on or above the diagonal are computed, for the rows
+ * i = row_first, row_first + row_step, ... < n (interleaved rows balance the triangle over row_step ranks; 1 rank:
+ * row_first 0, row_step 1).  The kernel's value for (i, j) is bit-identical to its value for (j, i), so mirroring the
+ * result reproduces the full matrix exactly at half the pair evaluations.
+ *   a [n,p,3] f32 -> out [n,n] f32 row-major, FULL-matrix indexing: out[i*n + j] written for owned i and j >= i only. */
+int ldt_pairwise_cd_upper(int n, int p, const float* a, int row_first, int row_step, float* out, void* stream);
 
 /* Approximate earth-mover distance (forward only).  Replaces approxmatch() + matchcost()
  * (evaluation/pytorch_structural_losses/src/approxmatch.cu:299-316), bound as StructuralLossesBackend.ApproxMatch /
@@ -145,7 +153,7 @@ int ldt_mlp_schedule_item(int tiles_m, int tn1, int tn2, int kb1, int kb2, int p
  * stage, [6] producer total, [7] tiles.  dev_buf must hold 8 * gridDim u64 (<= 8 * SM count).  NULL switches it off. */
 int ldt_debug_set_gemm_counters(unsigned long long* dev_buf);
 
-/* Diagnostics (tools/exp_gemm_limits.py only; results are WRONG while set): bit 0 = the CTA-pair GEMM skips its A
+/* Diagnostics (scripts/exp_gemm_limits.py only; results are WRONG while set): bit 0 = the CTA-pair GEMM skips its A
  * loads, bit 1 = skips its W loads (half the operand traffic either way), bit 2 = skips the epilogue, bit 3 = the fused
  * MLP kernel ignores its completion counters, bits 3-6 (with the counters on, GELU epilogue) = epilogue parts removed,
  * bit 8 = bf16 outputs through per-lane st.global instead of bulk tensor stores (results stay correct).  0 = off. */
@@ -232,11 +240,13 @@ enum ldt_predictor {
 
 /* offset_per_step: Philox offset advance per step (what torch adds per randn_like call), so step i of a
  * replayed CUDA graph uses offset + i*offset_per_step.  rng_grid: number of 256-thread blocks torch would
- * launch for `numel` elements on this device (<= 0 lets the library pick; only matters when z == NULL). */
+ * launch for `numel` elements on this device (<= 0 lets the library pick; only matters when z == NULL).
+ * rng_state (device u64[2] = {seed, base offset}, or NULL): added to the by-value seed / offset inside the kernel, so a
+ * captured CUDA graph can be replayed from any generator position.  x_next may alias x (in-place update). */
 int ldt_sde_step(int predictor, long long numel, const float* x, const float* params, const float* z,
                  const float* coef_table, const int* step_index /* device int, or NULL = 0 */,
                  unsigned long long seed, unsigned long long offset, unsigned long long offset_per_step,
-                 int rng_grid, float* x_next, float* x_mean, void* stream);
+                 const unsigned long long* rng_state, int rng_grid, float* x_next, float* x_mean, void* stream);
 
 /* PNDM pieces (diffusion_continuous.py:260-316).
  * ldt_pndm_transfer: out = x + coef[0] * (coef[1] * x - coef[2] * et)  -- transfer() :264-274; coef is a DEVICE array of

@@ -12,6 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libldt_b200.so")
+ABI_VERSION = 2   # == LDT_ABI_VERSION of include/ldt_b200.h (checked at load and in tests/test_abi_and_host.py)
 
 EPI_BIAS_F32 = 0
 EPI_BIAS_BF16 = 1
@@ -65,6 +66,7 @@ PROTOTYPES = {
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldt_pairwise_cd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p]),
+    "ldt_pairwise_cd_upper": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ldt_match_cost": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldt_approx_match": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldt_match_cost_from_match": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -92,7 +94,7 @@ PROTOTYPES = {
     "ldt_qkv_attention_bf16": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
     "ldt_sde_step": (C.c_int, [C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                               C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_void_p]),
     "ldt_pndm_transfer": (C.c_int, [C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldt_lincomb4": (C.c_int, [C.c_longlong, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_float,
@@ -126,7 +128,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError here means header/library mismatch
             fn.restype = res
             fn.argtypes = args
-        if lib.ldt_abi_version() != 1:
+        if lib.ldt_abi_version() != ABI_VERSION:
             raise RuntimeError("libldt_b200.so ABI version mismatch; rebuild with `python -m ldt_b200.build --force`")
         _lib = lib
     return _lib

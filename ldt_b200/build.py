@@ -41,7 +41,7 @@ def needs_build() -> bool:
 
 
 def build_variant(tag: str, defines: list[str]) -> str:
-    """Build ``libldt_b200_<tag>.so`` with extra ``-D`` defines (A/B experiments of kernel variants, tools/exp_ab_lib.py)."""
+    """Build ``libldt_b200_<tag>.so`` with extra ``-D`` defines (A/B experiments of kernel variants, scripts/exp_ab_lib.py)."""
     nvcc = _nvcc()
     objdir = os.path.join(CSRC, "build", tag)
     os.makedirs(objdir, exist_ok=True)

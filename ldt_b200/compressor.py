@@ -171,21 +171,40 @@ class Compressor(nn.Module):
         self._packed_key = None
 
     def reset_parameters(self):
-        """Own initialiser (the reference relies on torch's per-layer defaults; checkpoints overwrite either)."""
+        """torch's per-layer default initialisers drawn in the reference's CONSTRUCTION order (Network.py:125-157: input,
+        conv_in, group, pos_embedding, then encoder.i / decoder.i interleaved, output, init_set, pre_grouper), so that
+        ``torch.manual_seed(s); Compressor(cfg)`` yields the reference's random-init weights bit for bit (BASELINE
+        configs[0]: "random-init score net + Compressor decoder"; pinned by tests/golden/init_hashes.json).
+        Conv1d / Linear: kaiming_uniform(a=sqrt(5)) weight then U(-1/sqrt(fan_in), 1/sqrt(fan_in)) bias; LayerNorm /
+        BatchNorm / affine_alpha: ones and zeros; ActNorm: zeros; InitialSet.prior: U(0, 1) (Compressor/layers.py:24)."""
+        def group_of(name):
+            top = name.split(".")[0]
+            if top in ("encoder", "decoder"):
+                return (5, int(name.split(".")[1]), 0 if top == "encoder" else 1)
+            return ({"input": 0, "conv_in": 1, "group": 2, "pos_embedding": 3, "LabelEmbedding": 4, "output": 6,
+                     "init_set": 7}.get(top, 8), 0, 0)
+
+        params = dict(self.named_parameters())
         with torch.no_grad():
-            for name, p in self.named_parameters():
+            for name in sorted(params, key=group_of):   # stable: registration order inside each group
+                p = params[name]
                 if name.endswith("prior"):
-                    p.uniform_(0.0, 1.0)  # Compressor/layers.py:24
-                elif name.endswith("affine_alpha") or (p.dim() == 1 and "norm" in name and name.endswith("weight")) \
-                        or (".bn" in name and name.endswith("weight")) or name.endswith("net.1.weight") \
-                        or name.endswith("net1.1.weight"):
-                    p.fill_(1.0)
-                elif p.dim() >= 2 and name.endswith("weight"):
-                    fan_in = p[0].numel()
-                    bound = (1.0 / fan_in) ** 0.5
-                    p.uniform_(-bound, bound)
-                elif name.endswith("bias") and p.dim() == 1:
-                    p.uniform_(-0.05, 0.05)
+                    p.copy_(torch.rand(p.shape))
+                elif name.endswith("label_emb.weight"):
+                    p.normal_()
+                elif name.endswith(".weight") and p.dim() >= 2:
+                    nn.init.kaiming_uniform_(p, a=5 ** 0.5)
+                    bias = params.get(name[:-len("weight")] + "bias")
+                    if bias is not None:
+                        bound = (1.0 / p[0].numel()) ** 0.5
+                        bias.uniform_(-bound, bound)
+                elif name.endswith("affine_alpha") or (p.dim() == 1 and name.endswith(".weight")):
+                    p.fill_(1.0)      # LayerNorm / BatchNorm scale, grouper affine
+                elif name.endswith(".bias") and (name[:-len("bias")] + "weight") in params \
+                        and params[name[:-len("bias")] + "weight"].dim() >= 2:
+                    pass              # drawn together with its weight above
+                else:
+                    p.zero_()         # norm biases, affine_beta, ActNorm shift / log_scale
             for name, b in self.named_buffers():
                 if name.endswith("running_var"):
                     b.fill_(1.0)
@@ -208,8 +227,15 @@ class Compressor(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def _fingerprint(self):
-        return tuple((p.data_ptr(), p._version) for n, p in self.named_parameters()
-                     if n.startswith(("decoder.", "output.", "init_set.", "encoder.")))
+        return (getattr(self, "_generation", 0),) + tuple(
+            (p.data_ptr(), p._version) for n, p in self.named_parameters()
+            if n.startswith(("decoder.", "output.", "init_set.", "encoder.")))
+
+    def invalidate_packed(self) -> None:
+        """Drop the packed bf16 weights; needed only after in-place writes through ``.data`` (see Score.invalidate_packed)."""
+        self._packed = None
+        self._packed_key = None
+        self._generation = getattr(self, "_generation", 0) + 1
 
     def packed(self):
         key = self._fingerprint()

@@ -25,17 +25,23 @@ int check_cuda(cudaError_t e, const char* what, const char* file, int line) {
 
 void set_pdl(int on);
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev < LDT_MAX_DEVICES ? dev : LDT_MAX_DEVICES - 1;
+}
+
 int num_sms() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
+  static PerDevice<int> cached;   // zero-initialised: 0 = not queried on this device yet
+  int& c = cached.get();
+  if (c == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, current_device()) == cudaSuccess && n > 0)
+      c = n;
     else
-      cached = 148;  // B200
+      c = 148;  // B200
   }
-  return cached;
+  return c;
 }
 
 static int g_pdl = -1;

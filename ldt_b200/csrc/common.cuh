@@ -37,7 +37,24 @@ enum : int {
   LDT_ERR_WORKSPACE = -4, // caller-provided workspace too small
 };
 
-int  num_sms();           // cached cudaDevAttrMultiProcessorCount of the current device
+int  num_sms();           // cudaDevAttrMultiProcessorCount of the CURRENT device (cached per device)
+int  current_device();    // cudaGetDevice, clamped to [0, LDT_MAX_DEVICES)
+
+// One-time per-DEVICE set-up (cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to one device only, occupancy
+// and SM-count queries likewise): `static PerDevice<bool> done; if (!done.get()) { ...; done.get() = true; }`.
+constexpr int LDT_MAX_DEVICES = 64;
+template <typename T>
+struct PerDevice {
+  T v[LDT_MAX_DEVICES];
+  bool set[LDT_MAX_DEVICES];
+  T& get() { return v[current_device()]; }
+  // value with a sentinel default on first touch of a device
+  T& get_or(T init) {
+    const int d = current_device();
+    if (!set[d]) { v[d] = init; set[d] = true; }
+    return v[d];
+  }
+};
 bool pdl_enabled();       // programmatic dependent launch: off by default, on via ldt_set_pdl(1) or env LDT_PDL=1
 
 // ---- programmatic dependent launch (PDL) ----------------------------------------------------------

@@ -209,15 +209,24 @@ __device__ __forceinline__ void sde_update(float x, float prm, float z, const fl
   }
 }
 
+// x_next may alias x (the fused loop updates its state in place): every element is read before it is written by the
+// same thread and by no other, so neither pointer is declared __restrict__.
+// rng_state (device, or NULL): {seed, base offset} of the Philox stream, added to the by-value seed / offset.  A replayed
+// CUDA graph reads them at run time, so one capture serves every generator position.
 template <int PRED>
-__global__ void __launch_bounds__(256) sde_step_kernel(long long numel, const float* __restrict__ x,
+__global__ void __launch_bounds__(256) sde_step_kernel(long long numel, const float* x,
                                                      const float* __restrict__ params, const float* __restrict__ z,
                                                      const float* __restrict__ coef_table,
                                                      const int* __restrict__ step_index, unsigned long long seed,
                                                      unsigned long long offset, unsigned long long offset_per_step,
-                                                     float* __restrict__ x_next, float* __restrict__ x_mean) {
+                                                     const unsigned long long* __restrict__ rng_state,
+                                                     float* x_next, float* __restrict__ x_mean) {
   pdl_launch_dependents();
   pdl_wait();
+  if (rng_state != nullptr) {
+    seed += rng_state[0];
+    offset += rng_state[1];
+  }
   const int step = step_index ? *step_index : 0;
   const float* c = coef_table + static_cast<size_t>(step) * LDT_SDE_COEF_STRIDE;
   const long long T = static_cast<long long>(gridDim.x) * 256;
@@ -403,8 +412,8 @@ extern "C" int ldt_time_embedding(int R, int half, int D, const float* t, const 
 
 extern "C" int ldt_sde_step(int predictor, long long numel, const float* x, const float* params, const float* z,
                             const float* coef_table, const int* step_index, unsigned long long seed,
-                            unsigned long long offset, unsigned long long offset_per_step, int rng_grid, float* x_next,
-                            float* x_mean, void* stream) {
+                            unsigned long long offset, unsigned long long offset_per_step,
+                            const unsigned long long* rng_state, int rng_grid, float* x_next, float* x_mean, void* stream) {
   LDT_REQUIRE(numel >= 0, LDT_ERR_INVALID, "ldt_sde_step: negative numel");
   if (numel == 0) return LDT_OK;
   LDT_REQUIRE(x && params && coef_table && x_next, LDT_ERR_INVALID, "ldt_sde_step: null pointer");
@@ -413,7 +422,7 @@ extern "C" int ldt_sde_step(int predictor, long long numel, const float* x, cons
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define LDT_SDE_LAUNCH(P)                                                                                          \
   LDT_CUDA_OK(launch_pdl(sde_step_kernel<P>, dim3(grid), dim3(256), 0, s, numel, x, params, z, coef_table, step_index, \
-                         seed, offset, offset_per_step, x_next, x_mean))
+                         seed, offset, offset_per_step, rng_state, x_next, x_mean))
   switch (predictor) {
     case LDT_PRED_ANCESTRAL: LDT_SDE_LAUNCH(LDT_PRED_ANCESTRAL); break;
     case LDT_PRED_REVERSE_DIFFUSION: LDT_SDE_LAUNCH(LDT_PRED_REVERSE_DIFFUSION); break;

@@ -394,10 +394,10 @@ static int launch_approx_match(int pairs, int n, int m, const float* xyz1, const
   const size_t smem = static_cast<size_t>(n + m) * sizeof(float4);
 #define LDT_EMD_LAUNCH(P)                                                                                             \
   do {                                                                                                                \
-    static bool attr = false;                                                                                         \
-    if (!attr) {                                                                                                      \
+    static PerDevice<bool> attr;                                                                                      \
+    if (!attr.get()) {                                                                                                \
       LDT_CUDA_OK(cudaFuncSetAttribute(approx_match_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
-      attr = true;                                                                                                    \
+      attr.get() = true;                                                                                              \
     }                                                                                                                 \
     approx_match_kernel<P><<<pairs, EMD_THREADS, smem, s>>>(n, m, xyz1, xyz2, map, match, cost, cost_scale);          \
   } while (0)
@@ -407,10 +407,10 @@ static int launch_approx_match(int pairs, int n, int m, const float* xyz1, const
     scalar_only = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
   if (ppt == 2 && !scalar_only) {   // the 1025..2048-point case (ShapeNet clouds): packed-fp32 kernel
-    static bool attr = false;
-    if (!attr) {
+    static PerDevice<bool> attr;
+    if (!attr.get()) {
       LDT_CUDA_OK(cudaFuncSetAttribute(approx_match_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      attr = true;
+      attr.get() = true;
     }
     approx_match_x2_kernel<<<pairs, EMD_THREADS, 2 * smem, s>>>(n, m, xyz1, xyz2, map, match, cost, cost_scale);
   } else if (ppt <= 1) LDT_EMD_LAUNCH(1);

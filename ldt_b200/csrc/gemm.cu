@@ -179,7 +179,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // to ~110 (each tcgen05.mma / TMA wrapped in an ELECT + R2UR waterfall): the issuing warps share their schedulers with
 // two ALU-heavy epilogue warps each, and under that contention the long instruction chain per k-block, not the tensor
 // pipe, paced the mainloop (measured: MMA thread 10.4 k clk per 256x256x1024 tile with the GELU epilogue running,
-// 7.8 k without; tools/exp_gemm_limits.py).  DBG = per-role stall counters + the load/epilogue-skipping experiments.
+// 7.8 k without; scripts/exp_gemm_limits.py).  DBG = per-role stall counters + the load/epilogue-skipping experiments.
 template <int BN, int EPI, bool DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -394,7 +394,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // weight tile.  Each of the four CTAs fetches one quarter of the W tile (64 rows x 64 k) and TMA-multicasts it to the
 // CTA with the same rank-in-pair in the other pair, so a W byte crosses the L2->SM fabric once per 512 output rows
 // instead of once per 256: 48 KB instead of 64 KB per pair and k-block.  At the board's power cap the operand traffic
-// is a first-order energy term (tools/exp_sustained.py: the pair kernel with half of its loads removed runs 5-22 %
+// is a first-order energy term (scripts/exp_sustained.py: the pair kernel with half of its loads removed runs 5-22 %
 // faster), so fewer bytes is more clock.
 //   full[s]   leader of each pair   own pair's A (2 x 16 KB) + four W quarters landing in the pair (4 x 8 KB)
 //   empty[s]  every CTA, count 2    BOTH pairs' MMAs have released the stage (the sibling multicasts into our smem)
@@ -625,10 +625,10 @@ static int launch_tc(const ldt_gemm_args& a, const EpiParams& p, cudaStream_t s)
   if (rc) return rc;
   rc = make_tmap_bf16(&tmW, a.W, a.N, a.K, a.ldw, BN);
   if (rc) return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDevice<bool> attr_done;
+  if (!attr_done.get()) {
     LDT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
+    attr_done.get() = true;
   }
   const int tiles_m = (a.M + TC_BM - 1) / TC_BM;
   const int tiles_n = (a.N + BN - 1) / BN;
@@ -646,11 +646,11 @@ static int launch_tc2(const ldt_gemm_args& a, const EpiParams& p, cudaStream_t s
   if (rc) return rc;
   rc = make_tmap_bf16(&tmW, a.W, a.N, a.K, a.ldw, BN / 2);
   if (rc) return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDevice<bool> attr_done;
+  if (!attr_done.get()) {
     LDT_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     LDT_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
+    attr_done.get() = true;
   }
   const int tiles_m = (a.M + T2_BM - 1) / T2_BM;
   const int tiles_n = (a.N + BN - 1) / BN;
@@ -676,7 +676,8 @@ static int launch_tc2(const ldt_gemm_args& a, const EpiParams& p, cudaStream_t s
 template <int BN, int EPI>
 static int launch_tc4(const ldt_gemm_args& a, const EpiParams& p, cudaStream_t s) {
   using Cfg = Tc2Cfg<BN>;
-  static int max_clusters = -1;
+  static PerDevice<int> max_clusters_dev;
+  int& max_clusters = max_clusters_dev.get_or(-1);
   if (max_clusters < 0) {
     LDT_CUDA_OK(cudaFuncSetAttribute(gemm_tc4_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     cudaLaunchConfig_t cfg = {};

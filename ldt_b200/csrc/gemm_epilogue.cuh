@@ -138,7 +138,7 @@ __device__ __forceinline__ void epilogue_row32(const EpiParams& p, int row, int 
 // tm_out != nullptr (bf16 outputs): the staged 32-row x 64-column unit is written by ONE bulk tensor store issued by lane 0
 // (the staging layout IS the 128-byte TMA swizzle; the buffer must be 1024-byte aligned) instead of 8 ld.shared + 8
 // st.global per lane: the per-SM store path through the LSU was costing the fc1 epilogue as much as its GELU arithmetic
-// (tools/exp_epi.py).  The caller must run tma_store_wait_all()/..._read() on lane 0 before the buffer or the CTA goes away.
+// (scripts/exp_epi.py).  The caller must run tma_store_wait_all()/..._read() on lane 0 before the buffer or the CTA goes away.
 template <int EPI, int NCOLS, int XM = 0, typename WaitFn>
 __device__ __forceinline__ void epilogue_staged(const EpiParams& p, uint8_t* stg, int lane, int row_base, int col_base,
                                                 uint32_t taddr, WaitFn wait_accumulator, const CUtensorMap* tm_out = nullptr) {

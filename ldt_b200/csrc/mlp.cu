@@ -333,7 +333,8 @@ extern "C" int ldt_mlp_bf16(const ldt_mlp_args* args, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 
   using Cfg = Tc2Cfg<MLP_BN>;
-  static int max_pairs = -1;
+  static PerDevice<int> max_pairs_dev;
+  int& max_pairs = max_pairs_dev.get_or(-1);
   if (max_pairs < 0) {
     LDT_CUDA_OK(cudaFuncSetAttribute(mlp_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     // every CTA of the grid must be resident at once (tiles wait for tiles of other CTAs): ask the driver how many

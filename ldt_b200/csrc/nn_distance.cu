@@ -5,7 +5,7 @@
 // launched once per direction) and the Python double loop around it in
 // evaluation/evaluation_metrics.py:165-198 (_pairwise_CD_).
 //
-// Bit-exactness contract (checked in tests/test_nn_distance.py against oracle/nn_oracle.c and, on the
+// Bit-exactness contract (checked in tests/test_gpu_kernels.py against oracle/nn_oracle.c and, on the
 // GPU box, against the reference kernel itself built into oracle/_ref):
 //   d(p,q) = fma(dz,dz, fma(dx,dx, dy*dy))  with d* = q* - p*   -- the contraction nvcc 12.9 emits for
 //   the reference source line `x2*x2+y2*y2+z2*z2` (verified in its PTX); the squares make the sign of
@@ -129,20 +129,28 @@ constexpr int CD_THREADS = 256;
 constexpr int CD_QPT = 8;                         // query points per thread
 constexpr int CD_MAXP = CD_THREADS * CD_QPT;      // 2048 points per cloud handled in one pass
 
+// row_step / upper: the SYMMETRIC form (A == B, the rr / ss matrices of compute_CD_metrics, evaluation_metrics.py:311-312):
+// grid row y is cloud i = row_begin + y * row_step (rows interleaved over ranks balance the triangle), CTAs below the
+// diagonal (j < i) exit at once, and the result lands at out[i * ncols_out + j] of the FULL matrix; the caller mirrors.
+// Mirroring is exact, not approximate: the two sums below run over rowmin[] and colmin[] in the SAME index order, and
+// rowmin of (i, j) == colmin of (j, i) element for element (a minimum does not depend on evaluation order), so the kernel
+// returns M[i][j] == M[j][i] bit for bit whichever of the two it is asked for.
 __global__ void __launch_bounds__(CD_THREADS) pairwise_cd_kernel(int nb, int pa, int pb,
                                                                 const float* __restrict__ A,
                                                                 const float* __restrict__ B, int row_begin,
-                                                                int ncols_out, int col_begin,
+                                                                int ncols_out, int col_begin, int row_step, int upper,
                                                                 float* __restrict__ out) {
+  const int i = row_begin + blockIdx.y * row_step;
+  const int j = col_begin + blockIdx.x;
+  if (upper && j < i) return;
   extern __shared__ float4 cd_smem[];
   const int pb32 = (pb + 31) & ~31;                              // candidates padded to whole groups of 32
   float4* cand_xy = cd_smem;                                     // [pb32] (x, x, y, y)
   float2* cand_z = reinterpret_cast<float2*>(cand_xy + pb32);    // [pb32] (z, z)
   unsigned* colmin = reinterpret_cast<unsigned*>(cand_z + pb32); // [pb32]
+  float* rowmin = reinterpret_cast<float*>(colmin + pb32);       // [pa]
   __shared__ double red[2][CD_THREADS / 32];
 
-  const int i = row_begin + blockIdx.y;
-  const int j = col_begin + blockIdx.x;
   const float* a = A + static_cast<size_t>(i) * pa * 3;
   const float* b = B + static_cast<size_t>(j) * pb * 3;
   const int lane = threadIdx.x & 31;
@@ -157,7 +165,6 @@ __global__ void __launch_bounds__(CD_THREADS) pairwise_cd_kernel(int nb, int pa,
   }
   __syncthreads();
 
-  double row_sum = 0.0;
   // queries are processed in passes of CD_MAXP so any pa works; pa == 2048 is a single pass.
   for (int base = 0; base < pa; base += CD_MAXP) {
     float qx[CD_QPT], qy[CD_QPT], qz[CD_QPT], best[CD_QPT];
@@ -212,10 +219,12 @@ __global__ void __launch_bounds__(CD_THREADS) pairwise_cd_kernel(int nb, int pa,
     }
 #pragma unroll
     for (int u = 0; u < CD_QPT; ++u)
-      if (ok[u]) row_sum += static_cast<double>(best[u]);
+      if (ok[u]) rowmin[base + u * CD_THREADS + threadIdx.x] = best[u];
   }
   __syncthreads();
-  double col_sum = 0.0;
+  // both means are summed in the same (index-strided, then fixed tree) order: see the symmetry note above
+  double row_sum = 0.0, col_sum = 0.0;
+  for (int k = threadIdx.x; k < pa; k += CD_THREADS) row_sum += static_cast<double>(rowmin[k]);
   for (int k = threadIdx.x; k < pb; k += CD_THREADS) col_sum += static_cast<double>(__uint_as_float(colmin[k]));
 
   // block reduction (fixed order => deterministic)
@@ -238,7 +247,7 @@ __global__ void __launch_bounds__(CD_THREADS) pairwise_cd_kernel(int nb, int pa,
     // dl.mean(dim=1) + dr.mean(dim=1)  (evaluation_metrics.py:191): two fp32 means, one fp32 add
     const float ml = static_cast<float>(rs / static_cast<double>(pa));
     const float mr = static_cast<float>(cs / static_cast<double>(pb));
-    out[static_cast<size_t>(blockIdx.y) * ncols_out + blockIdx.x] = __fadd_rn(ml, mr);
+    out[static_cast<size_t>(upper ? i : static_cast<int>(blockIdx.y)) * ncols_out + blockIdx.x] = __fadd_rn(ml, mr);
   }
 }
 
@@ -250,7 +259,6 @@ extern "C" int ldt_nn_distance(int b, int n, const float* xyz1, int m, const flo
                                int* idx1, float* dist2, int* idx2, void* stream) {
   LDT_REQUIRE(b >= 0 && n >= 0 && m >= 0, LDT_ERR_INVALID, "ldt_nn_distance: negative size (b=%d n=%d m=%d)", b, n, m);
   if (b == 0) return LDT_OK;
-  LDT_REQUIRE(b <= 65535, LDT_ERR_INVALID, "ldt_nn_distance: batch %d exceeds 65535", b);
   LDT_REQUIRE((n == 0 || (xyz1 && dist1 && idx1)) && (m == 0 || (xyz2 && dist2 && idx2)), LDT_ERR_INVALID,
               "ldt_nn_distance: null pointer");
   // An empty candidate set has no nearest neighbour; the reference leaves its outputs unwritten
@@ -259,9 +267,34 @@ extern "C" int ldt_nn_distance(int b, int n, const float* xyz1, int m, const flo
   if (n == 0) return LDT_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int per_block = NN_THREADS * NN_QPT;
-  nn_argmin_kernel<<<dim3((n + per_block - 1) / per_block, b), NN_THREADS, 0, s>>>(n, xyz1, m, xyz2, dist1, idx1);
-  nn_argmin_kernel<<<dim3((m + per_block - 1) / per_block, b), NN_THREADS, 0, s>>>(m, xyz2, n, xyz1, dist2, idx2);
+  // grid.y <= 65535: larger batches go in chunks (the reference loops `for (int i = blockIdx.x; i < b; i += gridDim.x)`,
+  // nndistance.cu:5)
+  for (int b0 = 0; b0 < b; b0 += 32768) {
+    const int nb = min(32768, b - b0);
+    const float* x1 = xyz1 + static_cast<size_t>(b0) * n * 3;
+    const float* x2 = xyz2 + static_cast<size_t>(b0) * m * 3;
+    nn_argmin_kernel<<<dim3((n + per_block - 1) / per_block, nb), NN_THREADS, 0, s>>>(n, x1, m, x2, dist1 + static_cast<size_t>(b0) * n,
+                                                                                     idx1 + static_cast<size_t>(b0) * n);
+    nn_argmin_kernel<<<dim3((m + per_block - 1) / per_block, nb), NN_THREADS, 0, s>>>(m, x2, n, x1, dist2 + static_cast<size_t>(b0) * m,
+                                                                                     idx2 + static_cast<size_t>(b0) * m);
+  }
   LDT_CUDA_OK(cudaGetLastError());
+  return LDT_OK;
+}
+
+static size_t cd_smem_bytes(int pa, int pb) {
+  return static_cast<size_t>((pb + 31) & ~31) * (sizeof(float4) + sizeof(float2) + sizeof(unsigned)) +
+         static_cast<size_t>(pa) * sizeof(float);
+}
+
+static int cd_prepare(const char* who, int pa, int pb, size_t* smem) {
+  *smem = cd_smem_bytes(pa, pb);
+  LDT_REQUIRE(*smem <= 200 * 1024, LDT_ERR_UNSUPPORTED, "%s: pa=%d pb=%d need %zu B of shared memory", who, pa, pb, *smem);
+  static PerDevice<bool> attr_set;
+  if (!attr_set.get()) {
+    LDT_CUDA_OK(cudaFuncSetAttribute(pairwise_cd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set.get() = true;
+  }
   return LDT_OK;
 }
 
@@ -274,19 +307,34 @@ extern "C" int ldt_pairwise_cd(int na, int nb, int pa, int pb, const float* a, c
   const int rows = row_end - row_begin;
   if (rows == 0 || nb == 0) return LDT_OK;
   LDT_REQUIRE(a && b && out, LDT_ERR_INVALID, "ldt_pairwise_cd: null pointer");
-  const size_t smem = static_cast<size_t>((pb + 31) & ~31) * (sizeof(float4) + sizeof(float2) + sizeof(unsigned));
-  LDT_REQUIRE(smem <= 200 * 1024, LDT_ERR_UNSUPPORTED, "ldt_pairwise_cd: pb=%d needs %zu B of shared memory", pb, smem);
+  size_t smem = 0;
+  int rc = cd_prepare("ldt_pairwise_cd", pa, pb, &smem);
+  if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  static bool attr_set = false;
-  if (!attr_set) {
-    LDT_CUDA_OK(cudaFuncSetAttribute(pairwise_cd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
   // grid.y is limited to 65535 rows per launch; chunk if a caller ever exceeds it.
   for (int r0 = 0; r0 < rows; r0 += 32768) {
     const int nr = min(32768, rows - r0);
-    pairwise_cd_kernel<<<dim3(nb, nr), CD_THREADS, smem, s>>>(nb, pa, pb, a, b, row_begin + r0, nb, 0,
+    pairwise_cd_kernel<<<dim3(nb, nr), CD_THREADS, smem, s>>>(nb, pa, pb, a, b, row_begin + r0, nb, 0, 1, 0,
                                                               out + static_cast<size_t>(r0) * nb);
+  }
+  LDT_CUDA_OK(cudaGetLastError());
+  return LDT_OK;
+}
+
+extern "C" int ldt_pairwise_cd_upper(int n, int p, const float* a, int row_first, int row_step, float* out, void* stream) {
+  LDT_REQUIRE(n >= 0 && p > 0, LDT_ERR_INVALID, "ldt_pairwise_cd_upper: bad sizes n=%d p=%d", n, p);
+  LDT_REQUIRE(row_step >= 1 && 0 <= row_first && row_first < row_step, LDT_ERR_INVALID,
+              "ldt_pairwise_cd_upper: need 0 <= row_first (%d) < row_step (%d)", row_first, row_step);
+  if (n == 0 || row_first >= n) return LDT_OK;
+  LDT_REQUIRE(a && out, LDT_ERR_INVALID, "ldt_pairwise_cd_upper: null pointer");
+  size_t smem = 0;
+  int rc = cd_prepare("ldt_pairwise_cd_upper", p, p, &smem);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int rows = (n - row_first + row_step - 1) / row_step;   // rows row_first, row_first + row_step, ... < n
+  for (int r0 = 0; r0 < rows; r0 += 32768) {
+    const int nr = min(32768, rows - r0);
+    pairwise_cd_kernel<<<dim3(n, nr), CD_THREADS, smem, s>>>(n, p, p, a, a, row_first + r0 * row_step, n, 0, row_step, 1, out);
   }
   LDT_CUDA_OK(cudaGetLastError());
   return LDT_OK;

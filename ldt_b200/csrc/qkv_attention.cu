@@ -209,7 +209,7 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[set]), 0));
 
-#ifndef LDT_QA_SKIP_ATTN   // A/B builds only (tools/exp_ab_lib.py): how much of the kernel is the attention arithmetic
+#ifndef LDT_QA_SKIP_ATTN   // A/B builds only (scripts/exp_ab_lib.py): how much of the kernel is the attention arithmetic
       // ---- S = Q K^T (32 x 32), fragments from the staged tile ----
       float s[2][4][4];
 #pragma unroll
@@ -379,10 +379,10 @@ extern "C" int ldt_qkv_attention_bf16(int B, int H, int K, const void* A, int ld
   if (rc) return rc;
   rc = make_tmap_bf16(&tmW, Wp, H * QA_BN, K, ldw, QA_BN / 2);
   if (rc) return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDevice<bool> attr_done;
+  if (!attr_done.get()) {
     LDT_CUDA_OK(cudaFuncSetAttribute(qkv_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QA_SMEM_BYTES));
-    attr_done = true;
+    attr_done.get() = true;
   }
   QkvAttnParams p;
   p.M = M; p.H = H; p.bias = bias_p; p.out = static_cast<__nv_bfloat16*>(out);

@@ -34,12 +34,27 @@ def _rows(rows, n):
     return (0, n) if rows is None else rows
 
 
+def _same_set(a, b) -> bool:
+    """Both arguments are the same cloud set (the M_rr / M_ss calls, :311-312): the matrix is symmetric."""
+    return a is b or (a.shape == b.shape and a.dtype == b.dtype and a.device == b.device and a.data_ptr() == b.data_ptr()
+                      and a.stride() == b.stride())
+
+
 def _pairwise_CD_(sample_pcs, ref_pcs, batch_size=None, verbose=True, rows=None):
     """[N_sample, N_ref] matrix, entry (i, j) = CD(sample i, ref j).  ``rows=(begin, end)`` computes a row block
-    (used to shard the matrix over GPUs)."""
+    (used to shard the matrix over GPUs).
+
+    When both arguments are the same set (M_rr, M_ss) and the whole matrix is asked for, only the entries on or above the
+    diagonal are evaluated and mirrored: the kernel's (i, j) and (j, i) values are bit-identical (csrc/nn_distance.cu), so
+    the result equals the full evaluation the reference performs -- at half the pair evaluations.  The approximate EMD is
+    NOT symmetric (ApproxMatch treats its two sets differently, approxmatch.cu:3-182), so ``_pairwise_EMD_CD_`` mirrors
+    only its CD half."""
+    same = _same_set(sample_pcs, ref_pcs)
     a = sample_pcs.contiguous().float()
-    b = ref_pcs.contiguous().float()
     begin, end = _rows(rows, a.shape[0])
+    if same and rows is None:
+        return ops.mirror_upper(ops.pairwise_cd_upper(a))
+    b = a if same else ref_pcs.contiguous().float()
     return ops.pairwise_cd(a, b, begin, end)
 
 
@@ -48,7 +63,7 @@ def _pairwise_EMD_CD_(sample_pcs, ref_pcs, batch_size=None, accelerated_cd=True,
     a = sample_pcs.contiguous().float()
     b = ref_pcs.contiguous().float()
     begin, end = _rows(rows, a.shape[0])
-    return ops.pairwise_cd(a, b, begin, end), ops.pairwise_emd(a, b, begin, end)
+    return _pairwise_CD_(sample_pcs, ref_pcs, rows=rows), ops.pairwise_emd(a, b, begin, end)
 
 
 def knn(Mxx, Mxy, Myy, k, sqrt=False):

@@ -103,6 +103,31 @@ def pairwise_cd(a: torch.Tensor, b: torch.Tensor, row_begin: int = 0, row_end: i
     return out
 
 
+def pairwise_cd_upper(a: torch.Tensor, row_first: int = 0, row_step: int = 1, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Upper triangle (j >= i) of the [n,n] Chamfer matrix of cloud set a [n,p,3] against itself, for the rows
+    i = row_first, row_first + row_step, ...; written into ``out`` [n,n] (zeros where nothing is computed).  Mirror with
+    ``mirror_upper``: the kernel's (i,j) and (j,i) values are bit-identical."""
+    _req(a, torch.float32, "a")
+    if a.dim() != 3 or a.shape[2] != 3:
+        raise RuntimeError(f"expected [n,p,3], got {tuple(a.shape)}")
+    n, p = a.shape[0], a.shape[1]
+    if out is None:
+        out = torch.zeros((n, n), dtype=torch.float32, device=a.device)
+    else:
+        _req(out, torch.float32, "out")
+        if tuple(out.shape) != (n, n):
+            raise RuntimeError(f"out must be [{n},{n}], got {tuple(out.shape)}")
+    with torch.cuda.device(a.device), _launch("pairwise_cd"):
+        check(load().ldt_pairwise_cd_upper(n, p, ptr(a), row_first, row_step, ptr(out), stream_ptr()),
+              "ldt_pairwise_cd_upper")
+    return out
+
+
+def mirror_upper(u: torch.Tensor) -> torch.Tensor:
+    """Full symmetric matrix from its upper triangle (entries below the diagonal of ``u`` are ignored)."""
+    return torch.triu(u) + torch.triu(u, 1).t()
+
+
 def _check_sets(a, b, who):
     _req(a, torch.float32, "set_d")
     _req(b, torch.float32, "set_q")
@@ -265,11 +290,12 @@ def qkv_attention(B: int, H: int, A, Wp, bias_p, out) -> None:
 
 
 def sde_step(predictor: int, x, params, z, coef_table, step_index, seed: int, offset: int, offset_per_step: int,
-             rng_grid: int, x_next, x_mean) -> None:
+             rng_grid: int, x_next, x_mean, rng_state=None) -> None:
+    """rng_state: device int64[2] = {seed, base offset} (as unsigned bit patterns) added to seed / offset in the kernel."""
     with torch.cuda.device(x.device), _launch("sde_step"):
         check(load().ldt_sde_step(predictor, x.numel(), ptr(x), ptr(params), ptr(z), ptr(coef_table), ptr(step_index),
-                                  seed, offset, offset_per_step, rng_grid, ptr(x_next), ptr(x_mean), stream_ptr()),
-              "ldt_sde_step")
+                                  seed, offset, offset_per_step, ptr(rng_state), rng_grid, ptr(x_next), ptr(x_mean),
+                                  stream_ptr()), "ldt_sde_step")
 
 
 def pndm_transfer(x, et, coef, out) -> None:

@@ -14,6 +14,8 @@ issues ~700 kernel launches per step.  Three things make one captured step repla
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import ops
@@ -21,20 +23,50 @@ from ._lib import PRED_CORRECTOR
 from .sde import _PRED_CODES, torch_randn_launch_geometry
 
 
-def find_score_module(score_fn, sde):
+_warned: set = set()
+
+
+def _warn_once(key: str, msg: str) -> None:
+    if key not in _warned:
+        _warned.add(key)
+        import warnings
+        warnings.warn(msg, RuntimeWarning, stacklevel=3)
+
+
+def find_score_module(score_fn, sde, probe=None):
     """Return the ldt_b200.Score behind a Trainer.score_fn closure (trainer/Latent_SDE_Trainer.py:57-61), or None.
 
-    The fused loop hard-wires ``score = -params / sqrt(SDE.var(t))``; it is only taken when the callable is a bound
-    method named ``score_fn`` of an object whose ``.model`` is our Score and whose ``.SDE`` is this SDE object.
-    """
+    The fused loop hard-wires ``params = model(x, t, label, condition); score = -params / sqrt(SDE.var(t))``.  It is
+    taken only when (1) the callable is a bound method of an object whose ``.model`` is our Score and whose ``.SDE`` is
+    this SDE object (all three reference trainers), and (2) with ``probe = (t, x, label, condition)`` one real call of
+    ``score_fn`` returns exactly that pair, bit for bit -- a subclass that overrides ``score_fn`` (rescaled score,
+    guidance, another parameterisation) fails the probe and gets the generic per-step path with a one-time warning
+    instead of being silently replaced.  The probe draws no random numbers."""
     from .score import Score
     owner = getattr(score_fn, "__self__", None)
-    if owner is None or getattr(score_fn, "__name__", "") != "score_fn":
+    model = getattr(owner, "model", None) if owner is not None else None
+    if not isinstance(model, Score):
         return None
-    model = getattr(owner, "model", None)
-    if isinstance(model, Score) and getattr(owner, "SDE", None) is sde:
-        return model
-    return None
+    if getattr(owner, "SDE", None) is not sde:
+        _warn_once("sde", "ldt_b200: score_fn is bound to an ldt_b200.Score but to another SDE object; sampling runs "
+                          "the generic per-step path, not the fused CUDA-graph loop")
+        return None
+    if probe is not None:
+        t, x, label, condition = probe
+        try:
+            got = score_fn(t, x, label=label, condition=condition)
+            tx = t.to(x)
+            params = model(x, tx, label=label, condition=condition)
+            score = -params / torch.sqrt(sde.var(tx))[:, None, None]
+            ok = (isinstance(got, (tuple, list)) and len(got) == 2 and torch.equal(got[1], params)
+                  and torch.equal(got[0], score))
+        except Exception:   # a closure with another signature: not ours to fuse
+            ok = False
+        if not ok:
+            _warn_once("probe", "ldt_b200: score_fn does not compute (-model(x, t) / sqrt(SDE.var(t)), model(x, t)); sampling "
+                                "runs the generic per-step path, not the fused CUDA-graph loop")
+            return None
+    return model
 
 
 def modulation_table(score, P, timesteps: torch.Tensor, chunk: int = 256) -> torch.Tensor:
@@ -73,7 +105,7 @@ class StepGraph:
 
     def __init__(self, score, sde, B, N, predictor, time_eps, probability_flow, device, use_graph=True,
                  per_sample_c=False, cross_attention=False, corrector_steps=0, snr=0.0):
-        self.score, self.B, self.N = score, B, N
+        self.score, self.B, self.N = score, B, N   # (the plan cache holds the only strong reference to a plan)
         # AncestralCorrector (:212-229): corrector_steps extra (score evaluation + update) pairs per step, each with
         # its own randn_like draw, so one step consumes 1 + corrector_steps Philox launches' worth of offsets
         self.corrector_steps = corrector_steps
@@ -106,8 +138,10 @@ class StepGraph:
         self.step = torch.zeros(1, dtype=torch.int32, device=device)
         self.mod_cur = torch.empty((1, self.table.shape[1]), dtype=torch.float32, device=device)
         self.rng_grid, self.offset_per_step = torch_randn_launch_geometry(self.x.numel(), device)
-        self.seed = 0
-        self.offset = 0
+        # Philox {seed, base offset} live in device memory (read by ldt_sde_step at run time), so the step graph is
+        # captured once per plan and replayed from any generator position
+        self.rng_state = torch.zeros(2, dtype=torch.int64, device=device)
+        self.captures = 0
         self.graph = None
         self.use_graph = use_graph
 
@@ -132,32 +166,34 @@ class StepGraph:
         self.score.run_tokens(self.P, self.ws, self.x.view(B * T, D), mod, mod_stride, self.params.view(B * T, D),
                               self.kv_cond)
         draws = 1 + self.corrector_steps
-        ops.sde_step(self.code, self.x, self.params, None, self.coef, self.step, self.seed, self.offset,
-                     draws * self.offset_per_step, self.rng_grid, self.x, self.x_mean)
+        ops.sde_step(self.code, self.x, self.params, None, self.coef, self.step, 0, 0,
+                     draws * self.offset_per_step, self.rng_grid, self.x, self.x_mean, rng_state=self.rng_state)
         for j in range(self.corrector_steps):
             self.score.run_tokens(self.P, self.ws, self.x.view(B * T, D), mod, mod_stride, self.params.view(B * T, D),
                                   self.kv_cond)
-            ops.sde_step(PRED_CORRECTOR, self.x, self.params, None, self.ccoef, self.step, self.seed,
-                         self.offset + (1 + j) * self.offset_per_step, draws * self.offset_per_step, self.rng_grid,
-                         self.x, self.x_mean)
+            ops.sde_step(PRED_CORRECTOR, self.x, self.params, None, self.ccoef, self.step, 0,
+                         (1 + j) * self.offset_per_step, draws * self.offset_per_step, self.rng_grid,
+                         self.x, self.x_mean, rng_state=self.rng_state)
         ops.advance_step(self.step)
 
     def run(self, x0: torch.Tensor, seed: int, offset: int, record_every: int | None = None) -> list:
         """Run all N steps from x0 (copied into the loop buffer) with Philox (seed, offset).  With record_every = s
         returns the x_mean snapshots after steps s, 2s, ... (the print_steps trajectory, :239-257)."""
+        def i64(v):   # unsigned 64-bit pattern as the int64 torch stores
+            v &= (1 << 64) - 1
+            return v - (1 << 64) if v >= (1 << 63) else v
+
         self.x.copy_(x0)
         self.step.zero_()
+        self.rng_state.copy_(torch.tensor([i64(seed), i64(offset)], dtype=torch.int64))
         snaps = []
         if not self.use_graph:
-            self.seed, self.offset = seed, offset
             for i in range(self.N):
                 self._step_body()
                 if record_every and (i + 1) % record_every == 0:
                     snaps.append(self.x_mean.clone())
             return snaps
-        if self.graph is None or (seed, offset) != (self.seed, self.offset):
-            # seed/offset are baked into the captured kernel arguments: (re)capture for a new generator position
-            self.seed, self.offset = seed, offset
+        if self.graph is None:
             self._step_body()  # warm-up outside capture (lazy module loading, attribute setup)
             self.x.copy_(x0)
             self.step.zero_()
@@ -169,6 +205,7 @@ class StepGraph:
             self.launches_per_step = ops.launch_count() - n0
             ops.add_launches(-self.launches_per_step)  # captured, not executed
             self.graph = g
+            self.captures += 1
             # the capture itself does not execute; state is still (x0, step 0)
         for i in range(self.N):
             self.graph.replay()
@@ -190,13 +227,17 @@ def fused_sample_loop(score, sde, x0, N, predictor, time_eps, probability_flow, 
     device = x0.device
     B = x0.shape[0]
     per_sample_c, cross = extra is not None, cond_tokens is not None
-    key = (id(score), id(sde), B, N, predictor, float(time_eps), bool(probability_flow), device, use_graph,
+    key = (B, N, predictor, float(time_eps), bool(probability_flow), device, use_graph,
            per_sample_c, cross, corrector_steps, float(snr), score._fingerprint())
     sg = _graph_cache.get(key)
+    # the plan belongs to these two objects: weak references, not id() (an id can be reused after garbage collection)
+    if sg is not None and (sg.score_ref() is not score or sg.sde_ref() is not sde):
+        sg = None
     if sg is None:
         _graph_cache.clear()  # one live plan: the buffers are large (modulation table ~0.6 GB at N=1000)
         sg = StepGraph(score, sde, B, N, predictor, time_eps, probability_flow, device, use_graph,
                        per_sample_c=per_sample_c, cross_attention=cross, corrector_steps=corrector_steps, snr=snr)
+        sg.score_ref, sg.sde_ref = weakref.ref(score), weakref.ref(sde)
         _graph_cache[key] = sg
     if per_sample_c or cross:
         sg.set_condition(cond_tokens, extra)

@@ -181,7 +181,7 @@ class Score(nn.Module):
         # the MLP half of a block (fc1 + GELU -> fc2 + gate + residual) runs as ONE persistent kernel when the shapes fill
         # whole CTA-pair tiles (ops.mlp_supported).  Bit-identical to the two GEMM launches and 17 % faster than them at
         # boost clocks, but at the board's power cap the whole token pass measures the same (5.34 vs 5.31 ms, interleaved
-        # A/B, tools/exp_step_ab.py): the default stays with the two launches, which wait on nothing.
+        # A/B, scripts/exp_step_ab.py): the default stays with the two launches, which wait on nothing.
         self.fused_mlp = False
 
     # ------------------------------------------------------------------------------------------
@@ -194,7 +194,16 @@ class Score(nn.Module):
                 yield p
 
     def _fingerprint(self):
-        return tuple((p.data_ptr(), p._version) for p in self._hot_parameters())
+        return (getattr(self, "_generation", 0),) + tuple((p.data_ptr(), p._version) for p in self._hot_parameters())
+
+    def invalidate_packed(self) -> None:
+        """Drop the packed bf16 weights (and with them any cached sampler plan).  The cache key is (data_ptr, _version)
+        per parameter, which catches ``load_state_dict``, ``.to()``, optimizer steps and the reference's EMA swap
+        (``p.data = ...``), but NOT in-place writes through ``.data`` (``p.data.copy_()``, ``p.data.mul_()``): call this
+        after such an update."""
+        self._packed = None
+        self._packed_key = None
+        self._generation = getattr(self, "_generation", 0) + 1
 
     def packed(self):
         key = self._fingerprint()

@@ -229,9 +229,13 @@ class DiffusionVPSDE:
                 return x  # no predictor, no corrector: the loop is the identity (:243-249)
 
             from .sampler import fused_sample_loop, find_score_module  # late import (sampler imports Score)
-            score_mod = find_score_module(score_fn, self)
-            fusable = predictor is not None and (corrector is None or corrector == "ancestral")
-            if score_mod is not None and fusable and not isinstance(condition, dict):
+            fusable = (predictor is not None and (corrector is None or corrector == "ancestral")
+                       and not isinstance(condition, dict))
+            score_mod = None
+            if fusable:   # one real call of score_fn must reproduce what the fused step hard-wires (sampler.py)
+                probe_t = torch.ones((num_samples,), device=device) * torch.linspace(1.0, time_eps, N, device=device)[0]
+                score_mod = find_score_module(score_fn, self, probe=(probe_t, x, label, condition))
+            if score_mod is not None:
                 # the whole loop as one replayed graph; condition = (tokens | None, vector | 0.) as ConditionNet
                 # returns it (completion_trainer/Latent_SDE_Trainer.py:150-151), label -> embedding (score.py:125-126)
                 cond_tokens, extra = None, None

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Micro-benchmark of the dense-contraction core on the score net's four GEMM shapes (M = batch*32 rows).
 
-usage: python tools/bench_gemm.py [--batch 256] [--backends 2,3] [--reps 50]
+usage: python scripts/bench_gemm.py [--batch 256] [--backends 2,3] [--reps 50]
 Prints one line per (shape, backend): microseconds (CUDA events on the launching stream, L2 flushed by cycling
 through enough distinct operand sets to exceed the 126 MB L2 is NOT done here on purpose: inside the sampler the
 activations of one step are L2-resident, so this measures the same regime) and TFLOP/s.

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Sustained interleaved A/B of one GEMM shape under two ldt_debug_set_gemm_mode values (set at graph-capture time).
-usage: python tools/exp_ab_gemm.py modeA,modeB [shape ...]"""
+usage: python scripts/exp_ab_gemm.py modeA,modeB [shape ...]"""
 import os
 import sys
 
@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from ldt_b200 import _lib, ops  # noqa: E402
-from tools.exp_gemm_limits import graph_of, timed_with_clocks  # noqa: E402
+from scripts.exp_gemm_limits import graph_of, timed_with_clocks  # noqa: E402
 
 dev = torch.device("cuda:0")
 M = 8192

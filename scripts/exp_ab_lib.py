@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Sustained interleaved A/B of the product library against a variant build (ldt_b200.build.build_variant) on one GEMM
 shape.  Build the variant first (CPU container):  python -c "from ldt_b200.build import build_variant as b; b('alt', ['LDT_GELU_AS'])"
-usage: python tools/exp_ab_lib.py alt [shape ...]"""
+usage: python scripts/exp_ab_lib.py alt [shape ...]"""
 import ctypes as C
 import os
 import sys
@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from ldt_b200 import _lib, ops  # noqa: E402
-from tools.exp_gemm_limits import graph_of, timed_with_clocks  # noqa: E402
+from scripts.exp_gemm_limits import graph_of, timed_with_clocks  # noqa: E402
 
 dev = torch.device("cuda:0")
 M = 8192

@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from ldt_b200 import _lib, ops  # noqa: E402
-from tools.exp_gemm_limits import graph_of, timed_with_clocks  # noqa: E402
+from scripts.exp_gemm_limits import graph_of, timed_with_clocks  # noqa: E402
 
 dev = torch.device("cuda:0")
 M, N, K = 8192, 4096, 1024

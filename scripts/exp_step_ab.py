@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A/B of whole token passes (24 blocks, batch 256) as replayed CUDA graphs, interleaved A B A B ... so that thermal /
-power-cap drift hits both arms alike.  usage: python tools/exp_step_ab.py attr=valueA,valueB [rounds]
+power-cap drift hits both arms alike.  usage: python scripts/exp_step_ab.py attr=valueA,valueB [rounds]
    e.g. fused_mlp=0,1      (Score attribute toggled between the arms)
         env:LDT_X=0,1      (environment variable read at capture time)"""
 import os
@@ -12,7 +12,7 @@ import torch  # noqa: E402
 
 from ldt_b200 import Score  # noqa: E402
 from tests.helpers import airplane_config, ns  # noqa: E402
-from tools.exp_gemm_limits import timed_with_clocks  # noqa: E402
+from scripts.exp_gemm_limits import timed_with_clocks  # noqa: E402
 
 dev = torch.device("cuda:0")
 B = int(os.environ.get("AB_BATCH", "256"))

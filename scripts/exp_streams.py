@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Experiment: run the sampler as `chains` independent sub-batch chains on separate CUDA streams (each its own
 captured step graph) and report clouds/s.  Used to decide whether kernel-level concurrency hides wave quantisation,
-launch gaps and exposed epilogue tails.  usage: python tools/exp_streams.py --batch 256 --chains 1,2,4 --sde-steps 200
+launch gaps and exposed epilogue tails.  usage: python scripts/exp_streams.py --batch 256 --chains 1,2,4 --sde-steps 200
 """
 import argparse
 import os

@@ -4,7 +4,7 @@ CUDA graph and replayed for ~1.2 s while NVML samples SM clock and board power. 
 draws the same power, so time per launch is proportional to ENERGY per launch: this is the measurement that decides
 what to optimise (isolated 50-launch timings run at boost clocks and reward idle-time removal that the cap takes back).
 
-usage: python tools/exp_sustained.py [shape,...]     shapes: qkv fc_o fc1 fc2
+usage: python scripts/exp_sustained.py [shape,...]     shapes: qkv fc_o fc1 fc2
 """
 import os
 import sys
@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from ldt_b200 import _lib, ops  # noqa: E402
-from tools.exp_gemm_limits import graph_of, timed_with_clocks  # noqa: E402
+from scripts.exp_gemm_limits import graph_of, timed_with_clocks  # noqa: E402
 
 dev = torch.device("cuda:0")
 M = 8192

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Run on the GPU box via gpurun: every stage has its own timeout so a hung kernel cannot eat the lease.
-# usage: tools/gpu_check.sh [stage ...]   (default: all test stages)
+# usage: scripts/gpu_check.sh [stage ...]   (default: all test stages)
 set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.used --format=csv > gpurun_out/smi.txt 2>&1

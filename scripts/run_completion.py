@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """The completion workload alone (BASELINE configs[4] shape: ConditionNet prologue + conditional sampling + decode), for
-profiling under ncu.  usage: python tools/run_completion.py [sde_steps] [batch]"""
+profiling under ncu.  usage: python scripts/run_completion.py [sde_steps] [batch]"""
 import os
 import sys
 import time

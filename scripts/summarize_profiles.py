@@ -2,7 +2,7 @@
 """Turn the raw ncu artefacts of a gpurun call (gpurun_out/launches.csv, gpurun_out/prof_*.ncu-rep) into the small
 text summaries committed under profiles/ (named per round).  Runs in the build container (ncu -i needs no GPU).
 
-usage: python tools/summarize_profiles.py r01 [tag]
+usage: python scripts/summarize_profiles.py r01 [tag]
 """
 import collections
 import csv

@@ -56,8 +56,11 @@ from tests.helpers import airplane_config, small_score_cfg  # noqa: E402
 from tools.io import dict2namespace  # noqa: E402  (reference)
 
 
+OUT = os.environ.get("LDT_GOLDEN_OUT", HERE)   # tests/test_golden_recipe.py regenerates into a temp dir
+
+
 def save(name, **arrays):
-    path = os.path.join(HERE, name)
+    path = os.path.join(OUT, name)
     np.savez_compressed(path, **{k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in arrays.items()})
     print(f"wrote {name}: " + ", ".join(f"{k}{tuple(np.asarray(v).shape)}" for k, v in arrays.items()),
           f"({os.path.getsize(path) / 1024:.1f} KiB)")
@@ -259,6 +262,84 @@ def gen_sde():
         save("sde_ext.npz", **ext)
 
 
+def _sd_hash(module):
+    import hashlib
+    h = hashlib.sha256()
+    for k, v in module.state_dict().items():
+        h.update(k.encode())
+        h.update(v.detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+TRAJ_STEPS = (0, 1, 10, 100, 500, 998, 999)
+
+
+def gen_trajectory():
+    """BASELINE configs[0] run by the reference itself on CPU: common_init(0) -> Score(cfg.score), Compressor(cfg.compressor)
+    with torch's DEFAULT init (initialize_weights is never called, score.py:98), batch 16, the full 1000-step ancestral
+    loop (diffusion_continuous.py:152-162, 242-249) through the Trainer.score_fn closure (trainer/Latent_SDE_Trainer.py:
+    57-61), then Compressor.sample.  Stores, for steps TRAJ_STEPS, the loop state x_i, the noise drawn, params, x_mean and
+    x_next (SURVEY.md 8d teacher-forced parity inputs), the final latent and the decoded points -- never weights: both
+    sides rebuild them from the seed (init_hashes.json pins that they are the same bits).  ~15 min on 8 cores."""
+    import json
+    from diffusion.diffusion_continuous import DiffusionVPSDE
+    from model.Compressor.Network import Compressor
+    from model.scorenet.score import Score
+    cfg = dict2namespace(airplane_config())
+    B = 16
+    with CudaToCpu():
+        torch.manual_seed(0)                       # tools/utils.py:269-276 common_init(seed=0)
+        model = Score(cfg.score).eval()            # train_Latent_Diffusion.py:18-19 construction order
+        comp = Compressor(cfg.compressor).eval()
+        with open(os.path.join(OUT, "init_hashes.json"), "w") as f:
+            json.dump({"seed": 0, "score_sha256": _sd_hash(model), "compressor_sha256": _sd_hash(comp),
+                       "how": "sha256 over (key, fp32 bytes) of state_dict() after torch.manual_seed(0); Score(cfg.score); "
+                              "Compressor(cfg.compressor) with the reference modules"}, f, indent=1)
+        sde = DiffusionVPSDE(cfg.sde)
+        rec, call = {}, [0]
+
+        def score_fn(t, x, label=None, condition=None):   # trainer/Latent_SDE_Trainer.py:57-61
+            t = t.to(x)
+            params = model(x, t, label=label, condition=condition)
+            var = sde.var(t)[:, None, None]
+            i = call[0]
+            if i in TRAJ_STEPS:
+                rec[f"x_{i}"], rec[f"params_{i}"] = x.clone(), params.clone()
+            if i - 1 in TRAJ_STEPS:
+                rec[f"xnext_{i - 1}"] = x.clone()
+            call[0] += 1
+            if i % 50 == 0:
+                print("  step", i, flush=True)
+            return -params / torch.sqrt(var), params
+
+        real_randn_like = torch.randn_like
+
+        def rec_randn_like(x, *a, **k):
+            z = real_randn_like(x, *a, **k)
+            i = call[0] - 1
+            if i in TRAJ_STEPS:
+                rec[f"noise_{i}"] = z.clone()
+                rec[f"xmean_{i}"] = sys._getframe(1).f_locals["x_mean"].clone()   # Ancestral's local (:159)
+            return z
+
+        torch.manual_seed(1234)                    # SURVEY.md 8(d) row 1: sampling seed
+        torch.randn_like = rec_randn_like
+        try:
+            with torch.no_grad():
+                eps = sde.sample_discrete(score_fn=score_fn, num_samples=B, N=cfg.sde.sample_N, predictor="ancestral",
+                                          corrector=None, corrector_steps=1, shape=(cfg.score.z_scale, cfg.score.z_dim),
+                                          time_eps=cfg.sde.sample_time_eps, probability_flow=False, denoise=True,
+                                          snr=cfg.sde.snr, device="cpu")
+        finally:
+            torch.randn_like = real_randn_like
+        last = TRAJ_STEPS[-1]
+        rec[f"xnext_{last}"] = rec[f"xmean_{last}"] + torch.sqrt(sde.betas[0]) * rec[f"noise_{last}"]   # :161 (idx 0)
+        assert torch.equal(eps, rec[f"xmean_{last}"])
+        with torch.no_grad():
+            pts = comp.sample((B, 2048), given_eps=eps)   # trainer/Latent_SDE_Trainer.py:163 (CPU randperms follow on)
+    save("trajectory_b16.npz", eps=eps, points=pts, **rec)
+
+
 def gen_layout():
     """state_dict key -> shape of the reference modules for the shipped config (the checkpoint contract)."""
     import json
@@ -304,4 +385,4 @@ if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 1)
     which = sys.argv[1:] or ["score", "unet", "condition", "encoder", "decoder", "sde", "nn", "layout"]
     for w in which:
-        {"score": gen_score, "unet": gen_unet, "condition": gen_condition, "encoder": gen_encoder, "decoder": gen_decoder, "sde": gen_sde, "nn": gen_nn, "layout": gen_layout}[w]()
+        {"score": gen_score, "unet": gen_unet, "condition": gen_condition, "encoder": gen_encoder, "decoder": gen_decoder, "sde": gen_sde, "nn": gen_nn, "layout": gen_layout, "trajectory": gen_trajectory}[w]()

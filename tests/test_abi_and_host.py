@@ -31,7 +31,8 @@ def test_library_exports_every_declared_symbol():
     # and the ctypes prototypes cover exactly the declared entry points
     assert sorted(_lib.PROTOTYPES) == syms
     L = _lib.load()
-    assert L.ldt_abi_version() == 1
+    header = open(os.path.join(ROOT, "include", "ldt_b200.h")).read()
+    assert L.ldt_abi_version() == int(re.search(r"#define LDT_ABI_VERSION (\d+)", header).group(1)) == 2
     assert isinstance(L.ldt_last_error_string(), bytes)
 
 
@@ -49,7 +50,9 @@ def test_argument_validation_without_gpu():
     assert L.ldt_gemm_bf16(C.byref(a), None) == -1 and b"multiple of 64" in L.ldt_last_error_string()
     assert L.ldt_attention_nk32(1, 4, 32, 48, None, 0, None, None, 0, None, None) == -3
     assert L.ldt_layernorm_mod_bf16(4, 100, None, None, None, 0, 1, None, None, 1e-6, None, None) == -1
-    assert L.ldt_sde_step(9, 16, 1, 1, None, 1, None, 0, 0, 0, 0, 1, None, None) == -1
+    assert L.ldt_sde_step(9, 16, 1, 1, None, 1, None, 0, 0, 0, None, 0, 1, None, None) == -1
+    assert L.ldt_pairwise_cd_upper(8, 16, None, 2, 2, None, None) == -1 and b"row_first" in L.ldt_last_error_string()
+    assert L.ldt_pairwise_cd_upper(0, 16, None, 0, 1, None, None) == 0
 
 
 def test_state_dict_layout_matches_reference():

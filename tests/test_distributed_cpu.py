@@ -14,7 +14,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ldt_b200.distributed import gather_rows, shard_range
+from ldt_b200.distributed import gather_rows, interleaved_rows, shard_range, upper_pairs
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -53,7 +53,22 @@ def _worker(rank, world, port, na, nb, out_dir):
         s0, s1 = shard_range(total, world, rank)
         mine = torch.arange(s0, s1, dtype=torch.float32).view(-1, 1, 1).expand(-1, 4, 3).contiguous()
         clouds = gather_rows(mine, total)
-        torch.save({"full": full, "clouds": clouds}, os.path.join(out_dir, f"rank{rank}.pt"))
+        # (3) a set against itself: upper triangle on interleaved rows, gathered and mirrored.  The per-rank kernel call is
+        # stood in for by the oracle (this is the host logic; tests/test_gpu_distributed.py runs the real kernel per rank)
+        from ldt_b200 import distributed, ops
+
+        def fake_upper(x, row_first=0, row_step=1, out=None):
+            n = x.shape[0]
+            u = torch.zeros((n, n)) if out is None else out
+            for i in range(row_first, n, row_step):
+                row = torch.empty((1, n))
+                L.oracle_pairwise_cd(n, n, x.shape[1], x.shape[1], x.data_ptr(), x.data_ptr(), i, i + 1, row.data_ptr(), 1)
+                u[i, i:] = row[0, i:]
+            return u
+
+        ops.pairwise_cd_upper = fake_upper
+        sym = distributed.sharded_pairwise_cd(a, a)
+        torch.save({"full": full, "clouds": clouds, "sym": sym}, os.path.join(out_dir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -68,6 +83,19 @@ def test_shard_range_is_a_balanced_partition():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_interleaved_rows_balance_the_upper_triangle():
+    for total in (1, 7, 8, 2048, 2049):
+        for world in (1, 2, 3, 8):
+            rows = [list(interleaved_rows(total, world, r)) for r in range(world)]
+            assert sorted(i for rr in rows for i in rr) == list(range(total))
+            pairs = [upper_pairs(total, world, r) for r in range(world)]
+            assert sum(pairs) == total * (total + 1) // 2
+            assert max(pairs) - min(pairs) <= total        # within one row of each other
+    # BASELINE configs[3]: 2048 x 2048 over 8 ranks -> every rank evaluates exactly the same number of pairs
+    pairs = [upper_pairs(2048, 8, r) for r in range(8)]
+    assert max(pairs) == min(pairs)
+
+
 @pytest.mark.parametrize("na,nb", [(5, 3), (8, 8), (1, 4)])
 def test_two_rank_gloo_row_sharded_matrix_and_sample_gather(tmp_path, na, nb):
     world = 2
@@ -78,9 +106,13 @@ def test_two_rank_gloo_row_sharded_matrix_and_sample_gather(tmp_path, na, nb):
     b = torch.randn((nb, 48, 3), generator=g)
     ref = torch.empty((na, nb))
     _oracle().oracle_pairwise_cd(na, nb, 64, 48, a.data_ptr(), b.data_ptr(), 0, na, ref.data_ptr(), 1)
+    ref_sym = torch.empty((na, na))
+    _oracle().oracle_pairwise_cd(na, na, 64, 64, a.data_ptr(), a.data_ptr(), 0, na, ref_sym.data_ptr(), 1)
+    assert torch.equal(ref_sym, ref_sym.t())
     total = 2 * na + 1
     want = torch.arange(total, dtype=torch.float32).view(-1, 1, 1).expand(-1, 4, 3)
     for r in range(world):
         got = torch.load(os.path.join(str(tmp_path), f"rank{r}.pt"))
         assert torch.equal(got["full"], ref)          # bit-identical to the unsharded matrix, on every rank
         assert torch.equal(got["clouds"], want)
+        assert torch.equal(got["sym"], ref_sym)       # triangle on interleaved rows, gathered, mirrored == full matrix

@@ -144,6 +144,82 @@ def test_cd_metrics_match_reference_golden(dev):
     assert torch.allclose(M_rs, g["M_rs"], rtol=1e-4, atol=1e-6)
 
 
+def _unit_sphere_clouds(n, pts, seed):
+    """SURVEY.md 8(d) row 4 inputs: randn clouds centred and scaled to unit max-norm (ShapeNet_55.py:50-54)."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((n, pts, 3), generator=g)
+    x = x - x.mean(1, keepdim=True)
+    return x / x.norm(dim=-1).amax(1)[:, None, None]
+
+
+def test_pairwise_cd_values_at_2048_points(dev, oracle_nn):
+    """The headline CD size value-checked (not only properties): 4 x 4 clouds of 2048 points against (1) the C oracle and
+    (2) the reference's own NmDistanceKernel followed by torch's fp32 ``mean(dim=1)`` exactly as _pairwise_CD_ does
+    (evaluation_metrics.py:184-191).
+    Tolerances: (1) bit-exact -- same minima, both sums double-accumulated and rounded once.  (2) the reference rounds
+    every partial sum of its fp32 mean, ours is the correctly rounded mean: <= 4 ulp (rtol 5e-7) is stated; identical
+    minima mean cloud-level argmin / topk ties can only flip between entries closer than that."""
+    from ldt_b200 import ops
+    a, b = _unit_sphere_clouds(4, 2048, 7), _unit_sphere_clouds(4, 2048, 8)
+    M = ops.pairwise_cd(a.to(dev), b.to(dev)).cpu()
+    ref = torch.empty(4, 4)
+    oracle_nn.oracle_pairwise_cd(4, 4, 2048, 2048, a.data_ptr(), b.data_ptr(), 0, 4, ref.data_ptr(), 8)
+    assert torch.equal(M, ref)
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_nnd.so")
+    assert os.path.exists(path), "oracle/_ref/libref_nnd.so missing: run `make -C oracle` in the build container"
+    fn = getattr(C.CDLL(path), "_Z10nndistanceiiPKfiS0_PfPiS1_S2_P11CUstream_st")
+    fn.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_void_p] * 5
+    ad, bd = a.to(dev), b.to(dev)
+    rows = []
+    for i in range(4):   # the reference's loop: one row cloud expanded against a batch of column clouds
+        ai = ad[i:i + 1].expand(4, -1, -1).contiguous()
+        r1, r2 = torch.empty((4, 2048), device=dev), torch.empty((4, 2048), device=dev)
+        k1, k2 = torch.empty((4, 2048), dtype=torch.int32, device=dev), torch.empty((4, 2048), dtype=torch.int32, device=dev)
+        fn(4, 2048, ai.data_ptr(), 2048, bd.data_ptr(), r1.data_ptr(), k1.data_ptr(), r2.data_ptr(), k2.data_ptr(),
+           torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        rows.append((r1.mean(dim=1) + r2.mean(dim=1)).view(1, -1))
+    M_ref = torch.cat(rows, dim=0).cpu()
+    assert torch.allclose(M, M_ref, rtol=5e-7, atol=0)
+
+
+def test_pairwise_cd_upper_triangle_mirrors_to_the_full_matrix(dev):
+    """The symmetric form (M_rr / M_ss): upper triangle + mirror == the full N^2 evaluation, bit for bit, for every
+    interleaved row assignment (the multi-GPU split of SURVEY.md 8e)."""
+    from ldt_b200 import metrics, ops
+    for n, pts in ((24, 2048), (9, 300), (5, 2500)):
+        x = _unit_sphere_clouds(n, pts, 7 + n).to(dev)
+        full = ops.pairwise_cd(x, x)
+        assert torch.equal(full, full.t())
+        up = ops.pairwise_cd_upper(x)
+        assert torch.all(torch.tril(up, -1) == 0)                       # nothing below the diagonal is computed
+        assert torch.equal(ops.mirror_upper(up), full)
+        for world in (2, 3, 8):
+            acc = torch.zeros_like(full)
+            for r in range(world):
+                part = ops.pairwise_cd_upper(x, r, world)
+                owned = torch.zeros(n, dtype=torch.bool, device=dev)
+                owned[r::world] = True
+                assert torch.all(part[~owned] == 0)
+                acc += part
+            assert torch.equal(ops.mirror_upper(acc), full)
+        assert torch.equal(metrics._pairwise_CD_(x, x), full)           # the metrics entry point takes the triangle
+    with pytest.raises(RuntimeError, match="row_first"):
+        ops.pairwise_cd_upper(x, 3, 2)
+
+
+def test_compute_cd_metrics_evaluates_two_not_three_matrices(dev):
+    """compute_CD_metrics = N^2 (rs) + 2 * N(N+1)/2 (rr, ss upper triangles) pair evaluations; results unchanged."""
+    from ldt_b200 import metrics, ops
+    ref, smp = _unit_sphere_clouds(12, 256, 3).to(dev), (_unit_sphere_clouds(12, 256, 4) * 0.9).to(dev)
+    res = metrics.compute_CD_metrics(smp, ref)
+    M_rs, M_rr, M_ss = ops.pairwise_cd(ref, smp), ops.pairwise_cd(ref, ref), ops.pairwise_cd(smp, smp)
+    want = {}
+    metrics._update(want, metrics.lgan_mmd_cov(M_rs.t()), "CD")
+    metrics._update(want, metrics.knn(M_rr, M_rs, M_ss, 1, sqrt=False), "CD", only_acc=True)
+    assert set(res) == set(want) and all(torch.equal(res[k], want[k]) for k in want)
+
+
 # ------------------------------------------------------------------------------------------------
 # approximate EMD (ApproxMatch + MatchCost forward)
 # ------------------------------------------------------------------------------------------------
