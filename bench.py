@@ -44,12 +44,14 @@ def parse():
     ap.add_argument("--batch", type=int, default=256, help="clouds per GPU per step")
     ap.add_argument("--sde-steps", type=int, default=1000, help="reverse-SDE steps (config: 1000)")
     ap.add_argument("--points", type=int, default=2048)
-    ap.add_argument("--cd-clouds", type=int, default=192, help="clouds per set for the Chamfer-matrix metric")
+    ap.add_argument("--cd-clouds", type=int, default=2048, help="clouds per set for the Chamfer-matrix metric (configs[3]: 2048)")
     ap.add_argument("--emd-clouds", type=int, default=24, help="clouds per set for the approximate-EMD metric")
     ap.add_argument("--completion-batch", type=int, default=64, help="clouds per GPU of the completion workload")
     ap.add_argument("--no-secondary", action="store_true", help="skip the EMD / completion secondary metrics")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample-steps", type=int, default=20, help="score evaluations timed by the CPU arm (BASELINE.md 3: >= 20)")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the eager-PyTorch (oracle port on cuda) comparison")
+    ap.add_argument("--gpu-eager-steps", type=int, default=20)
     return ap.parse_args()
 
 
@@ -141,6 +143,51 @@ def cpu_reference_sample(batch, sde_steps_total, points, sample_steps, threads):
         t_dec = time.perf_counter() - t0
     total = sde_steps_total * t_step + t_dec
     return batch / total, t_step, t_dec
+
+
+def gpu_eager_baseline(dev, batch, sde_steps_total, points, steps):
+    """The reference's op sequence (oracle port: functional torch, one aten kernel per op like the reference's modules)
+    on the SAME GPU, fp32, with TF32 contraction allowed (torch's cuDNN-conv default the reference runs with) and not.
+    `steps` score evaluations + ancestral updates and one decode are CUDA-event timed at batch `batch` and extrapolated to
+    the full step count; context for the headline (expected O(10x)), not a target."""
+    from oracle import ldt_oracle as O
+    from ldt_b200.compressor import compressor_param_spec
+    from tests.test_oracle_golden import _score_shapes
+    c = ns(airplane_config())
+    sd = {k: v.to(dev) for k, v in O.synth_state_dict(_score_shapes(c.score), 12).items()}
+    csd = {k: v.to(dev) for k, v in O.synth_state_dict({k: v[0] for k, v in compressor_param_spec(c.compressor).items()}, 13).items()}
+    sde = O.VPSDE(c.sde.beta_start, c.sde.beta_end, c.sde.sigma2_0, c.sde.sample_N)
+    sde.betas = sde.betas.to(dev)
+    ts = torch.linspace(1.0, 1e-6, sde_steps_total, device=dev)
+    mask = torch.zeros((batch, c.compressor.max_outputs), dtype=torch.bool, device=dev)
+    out = {"what": "oracle port of the reference path (plain functional torch) on cuda:0, fp32 storage", "batch": batch,
+           "steps_timed": steps, "extrapolated_to_steps": sde_steps_total, "unit": "clouds/s"}
+    saved = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    try:
+        for tag, flag in (("tf32", True), ("fp32", False)):
+            torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = flag
+            x = torch.randn((batch, 32, 120), device=dev)
+            with torch.no_grad():
+                for i in range(2):   # warm-up
+                    vt = torch.ones(batch, device=dev) * ts[i]
+                    prm = O.score_forward(sd, c.score, x, vt)
+                torch.cuda.synchronize()
+                e0.record()
+                for i in range(steps):
+                    vt = torch.ones(batch, device=dev) * ts[i]
+                    prm = O.score_forward(sd, c.score, x, vt)
+                    x, xm = O.ancestral_step(sde, x, vt, prm, torch.randn_like(x), sde_steps_total)
+                e1.record()
+                O.decoder_sample(csd, c.compressor, xm, points, mask=mask)
+                e2.record()
+                torch.cuda.synchronize()
+            t_step, t_dec = e0.elapsed_time(e1) / 1e3 / steps, e1.elapsed_time(e2) / 1e3
+            out[tag] = {"value": batch / (sde_steps_total * t_step + t_dec), "ms_per_sde_step": 1e3 * t_step, "decode_s": t_dec,
+                        "allow_tf32": flag}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
+    return out
 
 
 def cpu_cd_pairs_per_s(threads, n=8, pts=2048):
@@ -293,57 +340,106 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_dev, t_e2e = float(tt[0]), float(tt[1])
 
-    # ---- roofline of the dominant kernel: eager pass over one SDE step with CUDA events around every GEMM ----
+    # ---- roofline: in-graph ablation of the step's kernel classes (ldt_b200/profiling.py) ----
     roof = None
-    cd = None
+    sus, burst, hbm, src = peaks()
     if rank == 0:
-        sus, burst, hbm, src = peaks()
         from ldt_b200 import profiling
-        prof = profiling.profile_score_step(model, B)
-        gemm_ms, gemm_flop = prof["gemm_ms"], prof["gemm_flop"]
-        achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12
+        abl = profiling.ablate_score_step(model, B)
+        achieved = abl["tensor_flop"] / (abl["tensor_ms"] * 1e-3) / 1e12
         step_flop = B * (N * FLOP_SCORE_PER_SAMPLE_STEP + FLOP_DECODE_PER_CLOUD)
-        traffic = None
+        traffic, traffic_src = None, None
         try:   # per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture (profiles/)
             import glob
             tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic*.json")))[-1]
             traffic = json.load(open(tf))["gemm_tc2_kernel"]["dram_bytes_per_launch"]
+            traffic_src = os.path.relpath(tf, ROOT) + " (ncu --set full capture of the same shape; not re-measured in this run)"
         except Exception:
             pass
-        roof = {"bound": "tensor", "achieved": achieved, "peak": sus, "unit": "TFLOP/s", "frac": achieved / sus, "traffic": traffic,
-                "kernel": "gemm_tc2_kernel + qkv_attention_kernel (tcgen05.mma.cta_group::2 256-row tiles, TMEM accumulators, TMA-fed, bulk-store epilogues)", "peak_source": src + ", sustained figure",
-                "launches_timed": prof["gemm_launches"], "gemm_share_of_step": prof["gemm_ms"] / prof["total_ms"],
+        per_kernel = {}
+        for cname, e in abl["classes"].items():
+            d = {"launches_per_step": e["launches"], "marginal_ms_per_step": round(e["marginal_ms"], 4),
+                 "us_per_launch": round(e["us_per_launch"], 2)}
+            if e.get("tflops") is not None:
+                d.update(bound="tensor", achieved_tflops=round(e["tflops"], 1), frac=round(e["tflops"] / sus, 4))
+            elif e.get("gbytes_per_s") is not None:
+                d.update(bound="hbm/l2", achieved_gbs=round(e["gbytes_per_s"], 1), frac=round(e["gbytes_per_s"] / hbm, 4),
+                         note="algorithmic bytes (f32 row in + bf16 row out) / marginal time; the rows are L2-resident between "
+                              "kernels, so > 1.0 of the HBM copy peak is possible")
+            per_kernel[cname] = d
+        roof = {"bound": "tensor", "achieved": achieved, "peak": sus, "unit": "TFLOP/s", "frac": achieved / sus,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "gemm_tc2_kernel + qkv_attention_kernel (tcgen05.mma.cta_group::2 256-row tiles, TMEM accumulators, "
+                          "TMA-fed, bulk-store epilogues)",
+                "peak_source": src + ", sustained figure (the kernels run inside a seconds-long power-capped step)",
+                "method": "in-graph ablation: the 24-block token pass captured in a CUDA graph and replayed, re-captured with one "
+                          "kernel class removed; marginal = full - without; sum(marginals) <= token pass by construction",
+                "token_pass_ms": round(abl["token_pass_ms"], 4), "sum_marginal_ms": round(abl["sum_marginal_ms"], 4),
+                "residual_ms": round(abl["residual_ms"], 4), "per_kernel": per_kernel,
                 "whole_step_achieved": step_flop * args.steps / t_dev / 1e12,
-                "whole_step_frac": step_flop * args.steps / t_dev / 1e12 / sus,
-                "per_kernel_ms": prof["by_kind"]}
-        # ---- secondary metric: Chamfer cloud-pairs/s ----
-        n = args.cd_clouds
-        g = torch.Generator().manual_seed(7)
-        a = torch.randn((n, P, 3), generator=g).to(dev)
-        b = torch.randn((n, P, 3), generator=g).to(dev)
-        ops.pairwise_cd(a, b)
-        torch.cuda.synchronize()
-        ev0.record()
-        reps = 3
-        for _ in range(reps):
-            ops.pairwise_cd(a, b)
-        ev1.record()
-        torch.cuda.synchronize()
-        t_cd = ev0.elapsed_time(ev1) / 1e3 / reps
-        pair_evals = n * n * P * P
-        cd = {"metric": "CD cloud-pairs/sec @2048x2048 pts", "value": n * n / t_cd, "unit": "pairs/s", "matrix": f"{n}x{n}",
-              "point_pair_evals_per_s": pair_evals / t_cd,
-              "roofline": {"bound": "fp32-issue", "achieved": pair_evals * 8 / t_cd / 1e12, "unit": "TFLOP/s (8 flop per point pair, each pair once)",
-                           "peak": 148 * 128 * 2 * 1.965e9 / 1e12, "peak_source": "nominal: 148 SMs x 128 FP32 lanes x 2 x 1.965 GHz",
-                           "frac": pair_evals * 8 / t_cd / (148 * 128 * 2 * 1.965e9)}}
+                "whole_step_frac": step_flop * args.steps / t_dev / 1e12 / sus}
 
-    # ---- secondary: approximate-EMD cloud-pairs/s and the completion workload (BASELINE configs[4]) ----
-    emd = completion = None
+    # ---- BASELINE configs[3]: 2048 x 2048 Chamfer matrix (2048 pts each), rows sharded over ALL ranks, NCCL gather ----
+    from ldt_b200.distributed import sharded_pairwise_cd
+    n = args.cd_clouds
+    gcd = torch.Generator().manual_seed(7)    # randn clouds centred, scaled to unit max-norm
+
+    def unit_clouds():
+        x = torch.randn((n, P, 3), generator=gcd)
+        x = x - x.mean(1, keepdim=True)
+        return (x / x.norm(dim=-1).amax(1)[:, None, None]).to(dev)
+
+    ref_c, smp_c = unit_clouds(), unit_clouds()
+    sharded_pairwise_cd(ref_c[:8 * world], smp_c[:8 * world])   # warm-up (attribute set-up, NCCL channels)
+    sharded_pairwise_cd(ref_c[:8 * world], ref_c[:8 * world])
+
+    def timed_cd(a, b):
+        barrier()
+        l_before = ops.launch_count()
+        ev0.record()
+        M = sharded_pairwise_cd(a, b)
+        ev1.record()
+        barrier()
+        tt = torch.tensor([ev0.elapsed_time(ev1) / 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return M, float(tt[0]), ops.launch_count() - l_before
+
+    M_rs, t_rs, l_rs = timed_cd(ref_c, smp_c)
+    M_rr, t_rr, l_rr = timed_cd(ref_c, ref_c)
+    cd = None
+    if rank == 0:
+        pair_evals = float(n) * n * P * P
+        fma_scalar = ops.measure_fma_peak(dev, packed=False)
+        fma_packed = ops.measure_fma_peak(dev, packed=True)
+        nominal = 148 * 128 * 2 * 1.965e9 / 1e12
+        cd_tf = pair_evals * 8 / t_rs / 1e12 / world     # per GPU
+        cd = {"metric": "CD cloud-pairs/sec @2048x2048 pts", "value": n * n / t_rs, "unit": "pairs/s", "matrix": f"{n}x{n}",
+              "points": P, "n_gpus": world, "seconds": t_rs, "rows": "contiguous row blocks per rank, all_gather of row blocks",
+              "workload": "BASELINE configs[3]: ref vs sample sets, seed 7, clouds centred and scaled to unit max-norm",
+              "point_pair_evals_per_s": pair_evals / t_rs, "kernel_launches": l_rs,
+              "symmetric": {"what": "M_rr (a set against itself): upper triangle on snake-interleaved rows + mirror, bit-identical "
+                                    "to the full matrix", "seconds": t_rr, "matrix_entries_per_s": n * n / t_rr,
+                            "pairs_evaluated": n * (n + 1) // 2, "equals_transpose": bool(torch.equal(M_rr, M_rr.t())),
+                            "zero_diagonal": bool(torch.all(M_rr.diagonal() == 0))},
+              "compute_CD_metrics_pair_evaluations": {"ours": n * n + n * (n + 1), "reference": 3 * n * n},
+              "roofline": {"bound": "fp32-pipe", "achieved": cd_tf, "unit": "TFLOP/s per GPU (8 flop per point pair, each pair once)",
+                           "peak": fma_scalar, "peak_source": "measured in this run: 8 independent fma.rn.f32 chains per thread "
+                                                              "(ldt_debug_fma_peak, csrc/diag.cu)",
+                           "frac": cd_tf / fma_scalar, "peak_packed_ffma2": fma_packed, "peak_nominal": nominal,
+                           "frac_of_nominal": cd_tf / nominal,
+                           "note": "the bit-exact distance is 3 sub + 1 mul + 2 fma = 8 flop in 6 FP32-pipe instructions "
+                                   "(3 packed, 2 lanes each) + 1 min per point pair; the FMA-only peak counts 2 flop per "
+                                   "instruction, so the structural ceiling of this formula is 8 / (7 x 2) = 0.57 of it"}}
+    del ref_c, smp_c, M_rs, M_rr
+
+    # ---- secondary: approximate-EMD cloud-pairs/s, rank 0 ----
+    emd = None
     if rank == 0 and not args.no_secondary:
-        n = args.emd_clouds
+        ne = args.emd_clouds
         g = torch.Generator().manual_seed(7)
-        a = torch.rand((n, P, 3), generator=g).to(dev)
-        b = torch.rand((n, P, 3), generator=g).to(dev)
+        a = torch.rand((ne, P, 3), generator=g).to(dev)
+        b = torch.rand((ne, P, 3), generator=g).to(dev)
         ops.pairwise_emd(a, b)
         torch.cuda.synchronize()
         ev0.record()
@@ -352,10 +448,14 @@ def main():
         torch.cuda.synchronize()
         t_emd = ev0.elapsed_time(ev1) / 1e3
         emd = {"metric": "approximate-EMD cloud-pairs/sec @2048x2048 pts (ApproxMatch + MatchCost forward)",
-               "value": n * n / t_emd, "unit": "pairs/s", "matrix": f"{n}x{n}"}
-        # completion: per-sample conditioning (image vector + 32 condition tokens), cross-attention in even blocks;
-        # the ConditionNet prologue (FPS + k-NN kernels, torch layers) is inside the timed region, as in
-        # completion_trainer/Latent_SDE_Trainer.py:147-170.  512 clouds over 8 GPUs = 64 per GPU.
+               "value": ne * ne / t_emd, "unit": "pairs/s", "matrix": f"{ne}x{ne}"}
+
+    # ---- BASELINE configs[4]: completion sampling, 64 clouds per GPU on EVERY rank (512 over 8 GPUs) ----
+    completion = None
+    if not args.no_secondary:
+        # per-sample conditioning (image vector + 32 condition tokens), cross-attention in even blocks; the ConditionNet
+        # prologue (FPS + k-NN kernels, torch layers) is inside the timed region, as in
+        # completion_trainer/Latent_SDE_Trainer.py:147-170
         cc = ns(airplane_config())
         cc.score.condition = True
         torch.manual_seed(0)
@@ -363,7 +463,7 @@ def main():
         ctr = Trainer()
         ctr.model = cmodel
         Bc = args.completion_batch
-        g = torch.Generator().manual_seed(99)
+        g = torch.Generator().manual_seed(99 + rank)
         views = torch.rand((Bc, 3, 224, 224), generator=g).to(dev)
         part = torch.randn((Bc, 2048, 3), generator=g)
         part = (part / part.norm(dim=-1).max(dim=1)[0][:, None, None]).to(dev)
@@ -375,20 +475,38 @@ def main():
                                           shape=(c.score.z_scale, c.score.z_dim), time_eps=c.sde.sample_time_eps, label=None,
                                           denoise=c.sde.denoise, device=dev, num_samples=Bc, probability_flow=False,
                                           snr=c.sde.snr, condition=condition)
-                return comp.sample((Bc, P), given_eps=eps)
+                pts = comp.sample((Bc, P), given_eps=eps)
+                if world > 1:
+                    out = [torch.empty_like(pts) for _ in range(world)]
+                    dist.all_gather(out, pts)
+                return pts
 
         completion_step()
-        torch.cuda.synchronize()
+        barrier()
         ev0.record()
         completion_step()
         ev1.record()
-        torch.cuda.synchronize()
-        t_c = ev0.elapsed_time(ev1) / 1e3
+        barrier()
+        tt = torch.tensor([ev0.elapsed_time(ev1) / 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_c = float(tt[0])
         # 18.14 GFLOP per sample-step (+ per-sample adaLN, - K/V of the step-invariant condition tokens)
-        completion = {"metric": "completion clouds/sec (ConditionNet + conditional SDE sample + decode @2048 pts)",
-                      "value": Bc / t_c, "unit": "clouds/s", "batch_per_gpu": Bc, "sde_steps": N,
-                      "tensor_tflops": Bc * N * 18.14e9 / t_c / 1e12}
+        if rank == 0:
+            tf = Bc * N * 18.14e9 / t_c / 1e12
+            completion = {"metric": "completion clouds/sec (ConditionNet + conditional SDE sample + decode @2048 pts)",
+                          "value": world * Bc / t_c, "unit": "clouds/s", "batch_per_gpu": Bc, "n_gpus": world,
+                          "total_batch": world * Bc, "sde_steps": N, "tensor_tflops_per_gpu": tf, "frac_of_sustained_peak": tf / sus,
+                          "workload": "BASELINE configs[4] shape: 512 clouds over 8 GPUs = 64 per GPU, every rank runs it"}
         del cmodel
+
+    # ---- the reference's arithmetic on this GPU: the oracle port (plain functional torch) on cuda, batch B, fp32 ----
+    gpu_eager = None
+    if rank == 0 and not args.no_gpu_eager:
+        try:
+            gpu_eager = gpu_eager_baseline(dev, B, N, P, args.gpu_eager_steps)
+        except Exception as e:   # context only: never take the bench line down
+            gpu_eager = {"error": repr(e)}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -412,7 +530,7 @@ def main():
             "e2e": {"value": clouds / t_e2e, "unit": "clouds/s", "h2d_bytes_per_step": B * 32 * 120 * 4,
                     "d2h_bytes_per_step": B * P * 3 * 4, "api": "DiffusionVPSDE.sample_discrete(score_fn=Trainer.score_fn) + Compressor.sample"},
             "gpu_launches": gpu_launches, "roofline": roof, "cpu_baseline": cpu, "cd": cd, "emd": emd,
-            "completion": completion, "clocks": clocks,
+            "completion": completion, "gpu_eager_baseline": gpu_eager, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -160,6 +160,12 @@ int ldt_debug_set_gemm_counters(unsigned long long* dev_buf);
 int ldt_debug_set_gemm_mode(int mode);
 int ldt_debug_get_gemm_mode(void);
 
+/* Diagnostics: a measured FP32-FMA rate for the Chamfer kernel's roofline (bench.py).  Launches blocks_per_sm * SMs blocks
+ * of 256 threads, each thread running `iters` rounds of 8 independent FMA chains: scalar fma.rn.f32 (packed = 0) or
+ * fma.rn.f32x2 (packed = 1).  *flop (host) receives the floating-point operations the launch performs; the caller times
+ * it with CUDA events.  out: any device float (never written in practice). */
+int ldt_debug_fma_peak(int iters, int packed, int blocks_per_sm, float* out, long long* flop, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Element-wise / normalisation kernels of the score net and decoder
  * ------------------------------------------------------------------------------------------------ */

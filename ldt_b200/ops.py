@@ -123,6 +123,24 @@ def pairwise_cd_upper(a: torch.Tensor, row_first: int = 0, row_step: int = 1, ou
     return out
 
 
+def measure_fma_peak(device, packed: bool, iters: int = 4096, blocks_per_sm: int = 8, reps: int = 5) -> float:
+    """Measured FP32 FMA rate in TFLOP/s on ``device`` (scalar FFMA or packed FFMA2 chains; csrc/diag.cu)."""
+    out = torch.zeros(1, dtype=torch.float32, device=device)
+    flop = C.c_longlong(0)
+    best = 0.0
+    with torch.cuda.device(device):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(reps + 1):
+            e0.record()
+            with _launch("fma_peak"):
+                check(load().ldt_debug_fma_peak(iters, int(packed), blocks_per_sm, ptr(out), C.byref(flop), stream_ptr()),
+                      "ldt_debug_fma_peak")
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, flop.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
 def mirror_upper(u: torch.Tensor) -> torch.Tensor:
     """Full symmetric matrix from its upper triangle (entries below the diagonal of ``u`` are ignored)."""
     return torch.triu(u) + torch.triu(u, 1).t()

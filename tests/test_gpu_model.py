@@ -345,8 +345,10 @@ def test_overridden_score_fn_is_probed_and_not_silently_replaced(dev):
 # ------------------------------------------------------------------------------------------------
 TRAJ_STEPS = (0, 1, 10, 100, 500, 998, 999)
 # Achieved on B200 (profiles/r02_trajectory_parity.txt; bf16 operands, fp32 accumulate, default torch init):
-#   params: rms error / rms(params) <= 2.9e-3 at every step, worst element <= 1.6e-2 rms  -> bars at 2x
-TOL_TRAJ_RMS = 6e-3
+#   params: rms error / rms(params) 3.29e-3 .. 3.32e-3 at every step, worst element 1.34e-2 .. 1.66e-2 rms;
+#   x_mean / x_next from OUR params with the reference's noise: <= 3.8e-5 rms (the update divides the error by 1/beta)
+#   -> bars at 2x the measured values
+TOL_TRAJ_RMS = 7e-3
 TOL_TRAJ_MAX = 3.5e-2
 
 
@@ -388,13 +390,24 @@ def test_teacher_forced_parity_on_reference_trajectory_batch16_default_init(dev)
     for i, r, m, rm, rn in report:
         assert r < TOL_TRAJ_RMS and m < TOL_TRAJ_MAX, (i, r, m)
         assert rm < TOL_TRAJ_RMS and rn < TOL_TRAJ_RMS, (i, rm, rn)
-    # decode the reference's final latent: the CPU randperm stream continues from the sampler's, but at 2048 of 2048
-    # points the mask is all-true, so the output does not depend on it
+    # Decoder.  (a) a unit-scale latent (the loop's N(0,1) start) decoded by the reference: the bf16 bar.
+    with torch.no_grad():
+        pts0 = comp.sample((16, 2048), given_eps=g["x_0"].to(dev))
+    r0, m0 = rms_rel_err(pts0, g["points_x0"]), rel_rms_err(pts0, g["points_x0"])
+    print("decoded points of x_0 (unit-scale latent): rms %.3e  max/rms %.3e" % (r0, m0))
+    check_vs_fp32(pts0, g["points_x0"])
+    # (b) the reference's FINAL latent.  With random-init nets the 1000-step loop diverges (rms 278, max 1239), the
+    # decoder's softmaxes saturate to arg-max and the decode is ill-conditioned in ANY arithmetic (the fp32 oracle with
+    # another summation order is already 3.4e-2 max/rms away from the reference).  The bar here is therefore the noise
+    # floor of bf16 operands itself: the CPU oracle with the same rounding points, against the same reference.
     with torch.no_grad():
         pts = comp.sample((16, 2048), given_eps=g["eps"].to(dev))
-    rp, mp = rms_rel_err(pts, g["points"]), rel_rms_err(pts, g["points"])
-    print("decoded points: rms %.3e  max/rms %.3e" % (rp, mp))
-    assert rp < TOL_TRAJ_RMS and mp < TOL_TRAJ_MAX, (rp, mp)
+    csd = {k: v.detach().cpu() for k, v in comp.state_dict().items()}
+    emu = emulated(lambda: O.decoder_sample(csd, c.compressor, g["eps"], 2048))
+    rp, floor = rms_rel_err(pts, g["points"]), rms_rel_err(emu, g["points"])
+    print("decoded points of the final latent: rms %.3e vs reference (bf16-emulating oracle: %.3e); ours vs that oracle %.3e"
+          % (rp, floor, rms_rel_err(pts, emu)))
+    assert torch.isfinite(pts).all() and rp < 1.25 * floor, (rp, floor)
 
 
 def test_sample_then_decode_end_to_end_small_steps(dev):

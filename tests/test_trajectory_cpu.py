@@ -68,6 +68,16 @@ def test_oracle_reproduces_reference_trajectory_teacher_forced():
     assert torch.equal(g["xnext_0"], g["x_1"]) and torch.equal(g["xmean_999"], g["eps"])
 
 
+def test_oracle_decoder_reproduces_reference_decode_of_unit_scale_latent():
+    """Compressor.sample of the reference (default init, seed 0) on the loop's N(0,1) start latent, 2 clouds."""
+    g = golden("trajectory_b16.npz")
+    _, comp, c = default_init_modules()
+    csd = {k: v.detach() for k, v in comp.state_dict().items()}
+    with torch.no_grad():
+        pts = O.decoder_sample(csd, c.compressor, g["x_0"][:2], 2048)
+    assert rel_rms_err(pts, g["points_x0"][:2]) < 1e-4, rel_rms_err(pts, g["points_x0"][:2])
+
+
 @pytest.mark.skipif(not os.path.isdir(os.environ.get("LDT_REFERENCE", "/root/reference")),
                     reason="needs the reference tree (build container only)")
 def test_golden_recipe_runs_and_regenerates_committed_fixtures(tmp_path):
