@@ -206,6 +206,10 @@ int ldt_time_embedding(int R, int half, int D, const float* t, const float* freq
  * experiments/Hybrid_Trainer/airplane/config.yaml, served by a one-lane-per-query SIMT kernel). */
 int ldt_attention_nk32(int B, int H, int Nq, int dh, const void* q, int ldq, const void* k, const void* v,
                        int ldkv, void* o, void* stream);
+/* Which kernel serves ldt_attention_nk32: 0 (default) = S = Q K^T and O = P V as tcgen05.mma with TMEM accumulators
+ * (csrc/attention_tc.cu) for Nq == 32 or Nq >= 128 with dh in {32, 64}; 1 = the warp-level mma.sync kernels for every
+ * shape (the cross-check in tests).  Both round the un-normalised probabilities to bf16 at the same point. */
+int ldt_debug_set_attention_backend(int backend);
 
 /* The transposed shape: a SHORT query set over a LONG key set (Nq = 32 latent tokens attending to the Nk = 2048 decoded
  * points in DecoderBlock.compute_posterior, model/Compressor/Network.py:62-77), online softmax over key chunks.

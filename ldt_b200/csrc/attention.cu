@@ -295,7 +295,20 @@ attention_nk32_narrow_kernel(int units, int H, int Nq, int qtiles, const __nv_bf
 
 }  // namespace ldt
 
+namespace ldt {
+int attention_nk32_tc(int B, int H, int Nq, int dh, const void* q, int ldq, const void* k, const void* v, int ldkv, void* o,
+                      cudaStream_t s);   // attention_tc.cu
+}
+
 using namespace ldt;
+
+// 0 = tcgen05 kernel wherever it applies (Nq == 32 or Nq >= 128, dh in {32, 64}), 1 = the warp-level mma.sync kernels for
+// every shape (kept as the cross-check of the tcgen05 path in tests and for the shapes it does not take)
+static int g_attention_backend = 0;
+extern "C" int ldt_debug_set_attention_backend(int backend) {
+  g_attention_backend = backend;
+  return LDT_OK;
+}
 
 extern "C" int ldt_attention_nk32(int B, int H, int Nq, int dh, const void* q, int ldq, const void* k, const void* v,
                                   int ldkv, void* o, void* stream) {
@@ -308,12 +321,16 @@ extern "C" int ldt_attention_nk32(int B, int H, int Nq, int dh, const void* q, i
   LDT_REQUIRE((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
                reinterpret_cast<uintptr_t>(o)) % 16 == 0,
               LDT_ERR_INVALID, "ldt_attention_nk32: pointers must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (g_attention_backend == 0 && (dh == 32 || dh == 64) && (Nq == 32 || Nq >= 128)) {
+    const int rc = attention_nk32_tc(B, H, Nq, dh, q, ldq, k, v, ldkv, o, s);
+    if (rc != LDT_ERR_UNSUPPORTED) return rc;
+  }
   const int qtiles = (Nq + 31) / 32;
   const long long units = static_cast<long long>(B) * H * qtiles;
   LDT_REQUIRE(units < (1LL << 31), LDT_ERR_INVALID, "ldt_attention_nk32: too many work units");
   const int grid = static_cast<int>((units + ATT_WARPS - 1) / ATT_WARPS);
   const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(dh));
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dh == 8 || dh == 16) {
     auto* qq = static_cast<const __nv_bfloat16*>(q);
     auto* kk = static_cast<const __nv_bfloat16*>(k);

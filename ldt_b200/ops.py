@@ -293,6 +293,11 @@ def attention_nk32(B: int, H: int, Nq: int, dh: int, q, ldq: int, k, v, ldkv: in
               "ldt_attention_nk32")
 
 
+def set_attention_backend(backend: int) -> None:
+    """0 = tcgen05 attention kernel where it applies (default), 1 = warp-level mma.sync kernels (cross-check)."""
+    check(load().ldt_debug_set_attention_backend(int(backend)), "ldt_debug_set_attention_backend")
+
+
 def attention_longkv(B: int, H: int, Nq: int, Nk: int, dh: int, q, ldq: int, k, v, ldkv: int, o) -> None:
     with torch.cuda.device(o.device), _launch("attention_longkv"):
         check(load().ldt_attention_longkv(B, H, Nq, Nk, dh, ptr(q), ldq, ptr(k), ptr(v), ldkv, ptr(o), stream_ptr()),

@@ -507,6 +507,35 @@ def test_attention_with_reference_layout_quirk(dev, B, H, Nq, dh):
     assert rel_rms_err(o.float().view(B, Nq, C_), ref) < 3e-2
 
 
+@pytest.mark.parametrize("B,H,Nq,dh", [(3, 16, 32, 64), (9, 16, 32, 64), (2, 4, 2048, 32), (2, 4, 1000, 32), (1, 2, 128, 64),
+                                       (6, 4, 32, 32), (64, 16, 32, 64)])
+def test_tcgen05_attention_equals_mma_sync_attention(dev, B, H, Nq, dh):
+    """csrc/attention_tc.cu (S = Q K^T and O = P V as tcgen05.mma, block-diagonal P for four stacked samples) against the
+    warp-level mma.sync kernel on the same operands.  Both round exp2((s - max) * scale) to bf16 before P V and divide by
+    the fp32 row sum afterwards; what differs is the fp32 summation order inside the tensor core, i.e. a rare 1-ulp flip
+    of a bf16 probability or output."""
+    from ldt_b200 import ops
+    from ldt_b200.score import _PtrView
+    C_ = H * dh
+    g = torch.Generator().manual_seed(B * Nq + dh)
+    q = (torch.randn((B * Nq, C_), generator=g)).to(dev).bfloat16()
+    kv = (torch.randn((B * 32, 2 * C_), generator=g)).to(dev).bfloat16()
+    outs = []
+    try:
+        for backend in (1, 0):
+            ops.set_attention_backend(backend)
+            o = torch.full((B * Nq, C_), 7.0, dtype=torch.bfloat16, device=dev)
+            ops.attention_nk32(B, H, Nq, dh, q, C_, kv, _PtrView(kv.data_ptr() + 2 * C_), 2 * C_, o)
+            torch.cuda.synchronize()
+            outs.append(o.float())
+    finally:
+        ops.set_attention_backend(0)
+    sync, tc = outs
+    assert torch.isfinite(tc).all()
+    assert rms_rel_err(tc, sync) < 1.5e-3, rms_rel_err(tc, sync)
+    assert rel_rms_err(tc, sync) < 2e-2, rel_rms_err(tc, sync)
+
+
 @pytest.mark.parametrize("B", [1, 8, 13, 256])
 def test_fused_qkv_attention_equals_unfused_path(dev, B):
     """ldt_qkv_attention_bf16 (head-major packed weights, attention in the GEMM epilogue) against the unfused
