@@ -208,8 +208,10 @@ int ldt_attention_nk32(int B, int H, int Nq, int dh, const void* q, int ldq, con
                        int ldkv, void* o, void* stream);
 /* Which kernel serves ldt_attention_nk32: 0 (default) = S = Q K^T and O = P V as tcgen05.mma with TMEM accumulators
  * (csrc/attention_tc.cu) for Nq == 32 or Nq >= 128 with dh in {32, 64}; 1 = the warp-level mma.sync kernels for every
- * shape (the cross-check in tests).  Both round the un-normalised probabilities to bf16 at the same point. */
+ * shape (the cross-check in tests).  Both round the un-normalised probabilities to bf16 at the same point.  The fused
+ * projection + attention kernel (ldt_qkv_attention_bf16) follows the same switch. */
 int ldt_debug_set_attention_backend(int backend);
+int ldt_debug_get_attention_backend(void);
 
 /* The transposed shape: a SHORT query set over a LONG key set (Nq = 32 latent tokens attending to the Nk = 2048 decoded
  * points in DecoderBlock.compute_posterior, model/Compressor/Network.py:62-77), online softmax over key chunks.

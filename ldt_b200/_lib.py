@@ -67,6 +67,7 @@ PROTOTYPES = {
     "ldt_pairwise_cd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p]),
     "ldt_debug_set_attention_backend": (C.c_int, [C.c_int]),
+    "ldt_debug_get_attention_backend": (C.c_int, []),
     "ldt_debug_fma_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_longlong), C.c_void_p]),
     "ldt_pairwise_cd_upper": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ldt_match_cost": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -309,6 +309,7 @@ extern "C" int ldt_debug_set_attention_backend(int backend) {
   g_attention_backend = backend;
   return LDT_OK;
 }
+extern "C" int ldt_debug_get_attention_backend(void) { return g_attention_backend; }
 
 extern "C" int ldt_attention_nk32(int B, int H, int Nq, int dh, const void* q, int ldq, const void* k, const void* v,
                                   int ldkv, void* o, void* stream) {

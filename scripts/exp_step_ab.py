@@ -33,6 +33,9 @@ def main():
         if key == "gemm_mode":   # ldt_debug_set_gemm_mode value, read at capture time
             from ldt_b200 import _lib
             _lib.load().ldt_debug_set_gemm_mode(int(v))
+        elif key == "attn_backend":   # 0 = tcgen05 attention, 1 = mma.sync (ldt_debug_set_attention_backend), read at capture time
+            from ldt_b200 import ops
+            ops.set_attention_backend(int(v))
         elif key == "pdl":   # programmatic dependent launch on / off (ldt_set_pdl), read at capture time
             from ldt_b200 import _lib
             _lib.load().ldt_set_pdl(int(v))

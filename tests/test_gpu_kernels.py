@@ -561,6 +561,19 @@ def test_fused_qkv_attention_equals_unfused_path(dev, B):
     o = torch.full((M, Hd), 7.0, dtype=torch.bfloat16, device=dev)
     ops.qkv_attention(B, H, A, Wp, bp, o)
     assert rms_rel_err(o.float(), o_ref.float()) < 2e-3, rms_rel_err(o.float(), o_ref.float())
+    # the same fused kernel with the warp-level mma.sync attention arithmetic (the pre-tcgen05 epilogue, kept as a cross-check)
+    o_sync = torch.full((M, Hd), 7.0, dtype=torch.bfloat16, device=dev)
+    try:
+        ops.set_attention_backend(1)
+        ops.qkv_attention(B, H, A, Wp, bp, o_sync)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_attention_backend(0)
+    assert rms_rel_err(o.float(), o_sync.float()) < 1.5e-3, rms_rel_err(o.float(), o_sync.float())
+    assert rel_rms_err(o.float(), o_sync.float()) < 2e-2, rel_rms_err(o.float(), o_sync.float())
+    again = torch.empty_like(o)
+    ops.qkv_attention(B, H, A, Wp, bp, again)
+    assert torch.equal(again, o)     # run-to-run deterministic
     # fp32 formula on the bf16-rounded q/k/v
     q3 = qkv.float()
     qh = q3[:, :Hd].reshape(B, T, H, dh).permute(0, 2, 1, 3)
