@@ -84,7 +84,7 @@ int ldt_pairwise_emd(int na, int nb, int p, const float* a, const float* b, int 
  * Dense contraction core (used by the score net and the decoder; exported for parity tests)
  *   C[M,N] = epilogue( A[M,K] . W[N,K]^T + bias[N] )
  * A, W are bf16 K-major (row-major with K contiguous, leading dimensions lda/ldw in elements,
- * multiples of 8; K a multiple of 64).  W is exactly a Conv1d(k=1)/Linear weight [out,in].
+ * multiples of 8; K a multiple of 64) -- or f32 / TF32 with operand_type = 1.  W is exactly a Conv1d(k=1)/Linear weight [out,in].
  * This is what replaces every nn.Conv1d(k=1)/nn.Linear on the path (model/layers.py:159-161,
  * 120-124, 172, 238; model/scorenet/score.py:95; model/Compressor/Network.py:61,153).
  * ------------------------------------------------------------------------------------------------ */
@@ -94,6 +94,8 @@ enum ldt_epilogue {
   LDT_EPI_BIAS_GELU_BF16 = 2, /* out bf16 = gelu_erf(acc + bias)       (MLP fc, layers.py:127-128) */
   LDT_EPI_GATE_RESID_F32 = 3, /* out f32  = resid + gate[row/rows_per_gate] * (acc + bias); gate may
                                  be NULL (= 1): x + gate*f(x) of layers.py:218-219,225-226           */
+  LDT_EPI_BIAS_GELU_F32 = 4,  /* out f32  = tf32_round(gelu_erf(acc + bias)): the MLP hidden of the TF32 parity mode
+                                 (operand_type 1), rounded because it is the A operand of the next contraction */
 };
 
 typedef struct ldt_gemm_args {
@@ -114,6 +116,10 @@ typedef struct ldt_gemm_args {
   int backend;     /* 0 = tcgen05/TMEM/TMA kernel, tile shape chosen by the library (product path);
                       1 = naive SIMT cross-check kernel (tests only);
                       2 = force single-CTA 128-row tiles; 3 = force CTA-pair (cta_group::2) 256-row tiles */
+  int operand_type; /* 0 = A, W are bf16 (tcgen05 kind::f16; the product path);
+                       1 = A, W are f32 holding TF32-rounded values (tcgen05 kind::tf32, same pipeline, CTA-pair kernel
+                           only): the parity mode that matches the precision of the reference's own GPU arithmetic
+                           (cuDNN TF32 convolutions).  K a multiple of 32, lda / ldw multiples of 4; epilogues 0, 3, 4 */
 } ldt_gemm_args;
 
 int ldt_gemm_bf16(const ldt_gemm_args* args, void* stream);
@@ -194,6 +200,19 @@ int ldt_layernorm_mod_bf16(int rows, int C, const float* x, const float* shift, 
 int ldt_time_embedding(int R, int half, int D, const float* t, const float* freq, const float* w0,
                        const float* b0, const float* w1, const float* b1, const float* extra, float* c,
                        void* silu_c, float* scratch /* [R, D + 2*half] f32 */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * TF32 parity mode (Score.precision = "tf32"): fp32 activations, kind::tf32 contractions (ldt_gemm_bf16 with
+ * operand_type 1) -- the precision of the reference's own GPU path (cuDNN TF32 convolutions).  Plain SIMT kernels.
+ *   ldt_round_pad_tf32      out f32 [rows, ld_out] = tf32_round(silu ? SiLU(in) : in), zero-padded columns cols..ld_out
+ *   ldt_layernorm_mod_f32   ldt_layernorm_mod_bf16 with a TF32-rounded f32 output (any C)
+ *   ldt_attention_nk32_f32  ldt_attention_nk32 on f32 q/k/v (dh in {32, 64}), fp32 softmax, TF32-rounded f32 output
+ * ------------------------------------------------------------------------------------------------ */
+int ldt_round_pad_tf32(long long rows, int cols, const float* in, int ld_in, float* out, int ld_out, int silu, void* stream);
+int ldt_layernorm_mod_f32(int rows, int C, const float* x, const float* shift, const float* scale, long long mod_stride,
+                          int rows_per_mod, const float* weight, const float* bias, float eps, float* y, void* stream);
+int ldt_attention_nk32_f32(int B, int H, int Nq, int dh, const float* q, int ldq, const float* k, const float* v, int ldkv,
+                           float* o, void* stream);
 
 /* Multi-head attention over a short key set, one (batch, head) pair per warp group.
  *   q  bf16 [B*Nq, ldq]  (head h uses columns h*dh..h*dh+dh-1 -- contiguous channel groups,

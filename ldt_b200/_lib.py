@@ -18,6 +18,7 @@ EPI_BIAS_F32 = 0
 EPI_BIAS_BF16 = 1
 EPI_BIAS_GELU_BF16 = 2
 EPI_GATE_RESID_F32 = 3
+EPI_BIAS_GELU_F32 = 4
 
 PRED_ANCESTRAL = 0
 PRED_REVERSE_DIFFUSION = 1
@@ -40,6 +41,7 @@ class GemmArgs(C.Structure):
         ("gate_stride", C.c_longlong),
         ("rows_per_gate", C.c_int),
         ("backend", C.c_int),
+        ("operand_type", C.c_int),
     ]
 
 
@@ -68,6 +70,11 @@ PROTOTYPES = {
                                   C.c_void_p, C.c_void_p]),
     "ldt_debug_set_attention_backend": (C.c_int, [C.c_int]),
     "ldt_debug_get_attention_backend": (C.c_int, []),
+    "ldt_round_pad_tf32": (C.c_int, [C.c_longlong, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "ldt_layernorm_mod_f32": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
+    "ldt_attention_nk32_f32": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_int, C.c_void_p, C.c_void_p]),
     "ldt_debug_fma_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_longlong), C.c_void_p]),
     "ldt_pairwise_cd_upper": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ldt_match_cost": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

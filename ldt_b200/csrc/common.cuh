@@ -319,6 +319,19 @@ __device__ __forceinline__ void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t desc
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same with fp32 operands read as TF32 (kind::tf32: 8 K-elements = 32 bytes per instruction; the low 13 mantissa bits
+// of each operand are ignored by the tensor core, so producers round to TF32 first -- round_tf32 below).
+__device__ __forceinline__ void umma_tf32_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // accumulate form without the predicate set-up (every k-slice after the first of a tile)
 __device__ __forceinline__ void umma_bf16_ss_pair_acc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
   asm volatile(
@@ -361,7 +374,22 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
          | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// Instruction descriptor: tf32 x tf32 -> fp32 (fp32 operands in shared memory), both operands K-major, tile M x N.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
+  return (1u << 4)                       // D format  = F32
+         | (2u << 7)                     // A format  = TF32
+         | (2u << 10)                    // B format  = TF32
+         | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
 // ---- math -----------------------------------------------------------------------------------------
+// fp32 -> nearest TF32 value (10 explicit mantissa bits), kept in an fp32 container: what cuBLAS / cuDNN feed their TF32
+// tensor-core paths (cvt.rna).  Operands of the kind::tf32 contractions are rounded once where they are produced.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

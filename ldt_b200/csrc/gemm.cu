@@ -180,7 +180,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // two ALU-heavy epilogue warps each, and under that contention the long instruction chain per k-block, not the tensor
 // pipe, paced the mainloop (measured: MMA thread 10.4 k clk per 256x256x1024 tile with the GELU epilogue running,
 // 7.8 k without; scripts/exp_gemm_limits.py).  DBG = per-role stall counters + the load/epilogue-skipping experiments.
-template <int BN, int EPI, bool DBG>
+// TF32 = true: fp32 operands through the same pipeline (kind::tf32): a stage is still 128 bytes of K per row (32 fp32
+// instead of 64 bf16) and four UMMAs of 32 bytes each, so only the tensor maps, the instruction and its descriptor differ.
+template <int BN, int EPI, bool DBG, bool TF32 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                 const __grid_constant__ CUtensorMap tmO, const EpiParams p, const int K, const int tiles_m, const int tiles_n) {
@@ -207,7 +209,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
   const int num_tiles = tiles_m * tiles_n;
-  const int num_kb = K / TC_BK;
+  constexpr int KB_ELEMS = TF32 ? TC_BK / 2 : TC_BK;   // K elements per 128-byte stage row
+  const int num_kb = K / KB_ELEMS;
 
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
@@ -257,9 +260,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (elect_one()) {
           if (rank == 0) mbar_expect_tx_u32(full0 + stage * 8, tx_bytes);
           if (!DBG || !(dbg_mode & 1))
-            tma_load_2d_pair_u32(sA0 + stage * Cfg::A_BYTES, &tmA, full0_leader + stage * 8, kb * TC_BK, m0);
+            tma_load_2d_pair_u32(sA0 + stage * Cfg::A_BYTES, &tmA, full0_leader + stage * 8, kb * KB_ELEMS, m0);
           if (!DBG || !(dbg_mode & 2))
-            tma_load_2d_pair_u32(sB0 + stage * Cfg::B_BYTES, &tmW, full0_leader + stage * 8, kb * TC_BK, n0);
+            tma_load_2d_pair_u32(sB0 + stage * Cfg::B_BYTES, &tmW, full0_leader + stage * 8, kb * KB_ELEMS, n0);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -274,7 +277,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 1) {
     // ---- MMA issuer (leader CTA; converged warp, one elected lane issues) ----
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(T2_BM, BN);
+      constexpr uint32_t idesc = TF32 ? umma_idesc_tf32(T2_BM, BN) : umma_idesc_bf16(T2_BM, BN);
       const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty), tfull0 = smem_u32(tfull), tempty0 = smem_u32(tempty);
       // descriptors of (stage 0, k-slice 0); the start-address field counts 16-byte units, so later stages / k-slices
       // are plain additions (shared-memory addresses stay below 256 KB: no carry out of the 14-bit field)
@@ -301,9 +304,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (elect_one()) {
             const uint64_t da = descA0 + static_cast<uint64_t>(stage * (Cfg::A_BYTES >> 4));
             const uint64_t db = descB0 + static_cast<uint64_t>(stage * (Cfg::B_BYTES >> 4));
-            umma_bf16_ss_pair(tmem_d, da, db, idesc, kb != 0 ? 1u : 0u);
+            if constexpr (TF32) {
+              umma_tf32_ss_pair(tmem_d, da, db, idesc, kb != 0 ? 1u : 0u);
 #pragma unroll
-            for (int k = 1; k < TC_BK / 16; ++k) umma_bf16_ss_pair_acc(tmem_d, da + 2 * k, db + 2 * k, idesc);
+              for (int k = 1; k < TC_BK / 16; ++k) umma_tf32_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, 1u);
+            } else {
+              umma_bf16_ss_pair(tmem_d, da, db, idesc, kb != 0 ? 1u : 0u);
+#pragma unroll
+              for (int k = 1; k < TC_BK / 16; ++k) umma_bf16_ss_pair_acc(tmem_d, da + 2 * k, db + 2 * k, idesc);
+            }
             umma_commit_pair_u32(empty0 + stage * 8, 0x3);   // frees the stage in both CTAs
           }
           __syncwarp();
@@ -617,6 +626,55 @@ int make_tmap_bf16(CUtensorMap* tm, const void* base, int rows, int cols, int ld
   return LDT_OK;
 }
 
+// f32 [rows, ld] row-major; tile box = box_rows x 32 columns (128 bytes), 128-byte swizzle, OOB reads give zero.
+int make_tmap_f32(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return LDT_ERR_CUDA;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(TC_BK / 2), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(f32) failed: CUresult %d (base=%p rows=%d cols=%d ld=%d box_rows=%d)", (int)r, base,
+                   rows, cols, ld, box_rows);
+    return LDT_ERR_CUDA;
+  }
+  return LDT_OK;
+}
+
+// TF32 parity mode: the CTA-pair kernel with fp32 operands (kind::tf32).
+template <int BN, int EPI>
+static int launch_tc2_tf32(const ldt_gemm_args& a, const EpiParams& p, cudaStream_t s) {
+  using Cfg = Tc2Cfg<BN>;
+  CUtensorMap tmA, tmW;
+  int rc = make_tmap_f32(&tmA, a.A, a.M, a.K, a.lda, 128);
+  if (rc) return rc;
+  rc = make_tmap_f32(&tmW, a.W, a.N, a.K, a.ldw, BN / 2);
+  if (rc) return rc;
+  static PerDevice<bool> attr_done;
+  if (!attr_done.get()) {
+    LDT_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EPI, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done.get() = true;
+  }
+  const int tiles_m = (a.M + T2_BM - 1) / T2_BM;
+  const int tiles_n = (a.N + BN - 1) / BN;
+  const int tiles = tiles_m * tiles_n, max_pairs = num_sms() / 2;
+  const int waves = (tiles + max_pairs - 1) / max_pairs;
+  const int pairs = (tiles + waves - 1) / waves;
+  LDT_CUDA_OK(launch_pdl(gemm_tc2_kernel<BN, EPI, false, true>, dim3(2 * pairs), dim3(TC_THREADS), Cfg::SMEM_BYTES, s, tmA, tmW, tmA, p,
+                         a.K, tiles_m, tiles_n));
+  return LDT_OK;
+}
+
+template <int EPI>
+static int launch_any_tf32(const ldt_gemm_args& a, const EpiParams& p, cudaStream_t s) {
+  if (a.N % 256 == 0) return launch_tc2_tf32<256, EPI>(a, p, s);
+  return launch_tc2_tf32<128, EPI>(a, p, s);
+}
+
 template <int BN, int EPI>
 static int launch_tc(const ldt_gemm_args& a, const EpiParams& p, cudaStream_t s) {
   using Cfg = TcCfg<BN>;
@@ -769,9 +827,16 @@ extern "C" int ldt_gemm_bf16(const ldt_gemm_args* args, void* stream) {
   LDT_REQUIRE(args != nullptr, LDT_ERR_INVALID, "ldt_gemm_bf16: null args");
   const ldt_gemm_args& a = *args;
   LDT_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, LDT_ERR_INVALID, "ldt_gemm_bf16: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
-  LDT_REQUIRE(a.K % TC_BK == 0, LDT_ERR_INVALID, "ldt_gemm_bf16: K=%d must be a multiple of %d (pad with zeros)", a.K, TC_BK);
+  const bool tf32 = a.operand_type == 1;
+  LDT_REQUIRE(a.operand_type == 0 || a.operand_type == 1, LDT_ERR_INVALID, "ldt_gemm_bf16: unknown operand_type %d", a.operand_type);
+  if (tf32) {
+    LDT_REQUIRE(a.K % (TC_BK / 2) == 0, LDT_ERR_INVALID, "ldt_gemm_bf16: K=%d must be a multiple of %d for f32 operands", a.K, TC_BK / 2);
+    LDT_REQUIRE(a.backend == 0 || a.backend == 3, LDT_ERR_UNSUPPORTED, "ldt_gemm_bf16: f32 operands run on the CTA-pair kernel only");
+    LDT_REQUIRE(a.lda % 4 == 0 && a.ldw % 4 == 0, LDT_ERR_INVALID, "ldt_gemm_bf16: lda=%d ldw=%d must be multiples of 4 for f32 operands", a.lda, a.ldw);
+  }
+  LDT_REQUIRE(tf32 || a.K % TC_BK == 0, LDT_ERR_INVALID, "ldt_gemm_bf16: K=%d must be a multiple of %d (pad with zeros)", a.K, TC_BK);
   LDT_REQUIRE(a.N % 8 == 0, LDT_ERR_INVALID, "ldt_gemm_bf16: N=%d must be a multiple of 8", a.N);
-  LDT_REQUIRE(a.lda >= a.K && a.ldw >= a.K && a.lda % 8 == 0 && a.ldw % 8 == 0, LDT_ERR_INVALID,
+  LDT_REQUIRE(a.lda >= a.K && a.ldw >= a.K && (tf32 || (a.lda % 8 == 0 && a.ldw % 8 == 0)), LDT_ERR_INVALID,
               "ldt_gemm_bf16: lda=%d ldw=%d must be >= K and multiples of 8", a.lda, a.ldw);
   LDT_REQUIRE(a.ldo >= a.N && a.ldo % 8 == 0, LDT_ERR_INVALID, "ldt_gemm_bf16: ldo=%d must be >= N and a multiple of 8", a.ldo);
   LDT_REQUIRE(a.A && a.W && a.out, LDT_ERR_INVALID, "ldt_gemm_bf16: null operand");
@@ -787,6 +852,20 @@ extern "C" int ldt_gemm_bf16(const ldt_gemm_args* args, void* stream) {
   p.dbg_mode = g_gemm_dbg_mode;
   p.tma_store = (g_gemm_dbg_mode & 256) ? 0 : 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (tf32) {
+    switch (a.epilogue) {
+      case LDT_EPI_BIAS_F32: return launch_any_tf32<LDT_EPI_BIAS_F32>(a, p, s);
+      case LDT_EPI_BIAS_GELU_F32: return launch_any_tf32<LDT_EPI_BIAS_GELU_F32>(a, p, s);
+      case LDT_EPI_GATE_RESID_F32:
+        LDT_REQUIRE(a.resid != nullptr, LDT_ERR_INVALID, "ldt_gemm_bf16: residual epilogue needs resid");
+        LDT_REQUIRE(a.gate == nullptr || a.gate_stride % 4 == 0, LDT_ERR_INVALID, "ldt_gemm_bf16: gate_stride must be a multiple of 4");
+        return launch_any_tf32<LDT_EPI_GATE_RESID_F32>(a, p, s);
+      default:
+        set_last_error("ldt_gemm_bf16: epilogue %d is not available for f32 operands (0, 3, 4 are)", a.epilogue);
+        return LDT_ERR_UNSUPPORTED;
+    }
+  }
+  LDT_REQUIRE(a.epilogue != LDT_EPI_BIAS_GELU_F32, LDT_ERR_UNSUPPORTED, "ldt_gemm_bf16: LDT_EPI_BIAS_GELU_F32 needs operand_type 1");
   switch (a.epilogue) {
     case LDT_EPI_BIAS_F32: return launch_any<LDT_EPI_BIAS_F32>(a, p, s);
     case LDT_EPI_BIAS_BF16: return launch_any<LDT_EPI_BIAS_BF16>(a, p, s);

@@ -69,6 +69,10 @@ __device__ __forceinline__ void epilogue_row32(const EpiParams& p, int row, int 
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
   }
+  if constexpr (EPI == LDT_EPI_BIAS_GELU_F32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = round_tf32(gelu_erf_f(v[j]));
+  }
   if constexpr (EPI == LDT_EPI_GATE_RESID_F32) {
     const float* res = p.resid + static_cast<size_t>(row) * p.ldo + col0;
     const float* g = p.gate ? p.gate + static_cast<long long>(row / p.rows_per_gate) * p.gate_stride + col0 : nullptr;
@@ -90,7 +94,7 @@ __device__ __forceinline__ void epilogue_row32(const EpiParams& p, int row, int 
         if (col0 + j < p.N) v[j] = res[j] + (g ? g[j] : 1.0f) * v[j];
     }
   }
-  if constexpr (EPI == LDT_EPI_BIAS_F32 || EPI == LDT_EPI_GATE_RESID_F32) {
+  if constexpr (EPI == LDT_EPI_BIAS_F32 || EPI == LDT_EPI_GATE_RESID_F32 || EPI == LDT_EPI_BIAS_GELU_F32) {
     float* o = static_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
     if (full) {
 #pragma unroll
@@ -146,7 +150,7 @@ __device__ __forceinline__ void epilogue_staged(const EpiParams& p, uint8_t* stg
   const uint32_t stg_u32 = smem_u32(stg);
   const uint32_t st_row = stg_u32 + static_cast<uint32_t>(lane) * 128u;   // staging row written by this lane
   const int rr0 = lane >> 3, cc = lane & 7;                                // read-back: row rr0 + 4*i, chunk cc
-  if constexpr (EPI == LDT_EPI_BIAS_F32 || EPI == LDT_EPI_GATE_RESID_F32) {
+  if constexpr (EPI == LDT_EPI_BIAS_F32 || EPI == LDT_EPI_GATE_RESID_F32 || EPI == LDT_EPI_BIAS_GELU_F32) {
     constexpr int NU = NCOLS / 32;
     // one gate row for the whole 32-row slab (rows_per_gate a multiple of 32, e.g. the 32 latent tokens of a sample)?
     const bool gate_uniform = (p.rows_per_gate & 31) == 0 && (row_base & 31) == 0;
@@ -229,6 +233,10 @@ __device__ __forceinline__ void epilogue_staged(const EpiParams& p, uint8_t* stg
               unpack_f32x2(lo, a4.x, a4.y);
               unpack_f32x2(hi, a4.z, a4.w);
 #endif
+              if constexpr (EPI == LDT_EPI_BIAS_GELU_F32) {   // TF32 parity mode: exact-erf GELU, rounded to TF32
+                a4.x = round_tf32(gelu_erf_f(a4.x)); a4.y = round_tf32(gelu_erf_f(a4.y));
+                a4.z = round_tf32(gelu_erf_f(a4.z)); a4.w = round_tf32(gelu_erf_f(a4.w));
+              }
               *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col) = a4;
             }
           }

@@ -9,7 +9,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_GATE_RESID_F32, GemmArgs, MlpArgs, check, load,
+from ._lib import (EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_BIAS_GELU_F32, EPI_GATE_RESID_F32, GemmArgs, MlpArgs, check, load,
                    ptr, stream_ptr)
 
 
@@ -201,8 +201,9 @@ def pairwise_emd(a: torch.Tensor, b: torch.Tensor, row_begin: int = 0, row_end: 
 def gemm(A: torch.Tensor, W: torch.Tensor, bias, out: torch.Tensor, epilogue: int, *, N: int | None = None,
          K: int | None = None, resid=None, gate=None, gate_stride: int = 0, rows_per_gate: int = 1,
          backend: int = 0) -> torch.Tensor:
-    """out = epilogue(A @ W[:N,:K].T + bias).  A bf16 [M, lda], W bf16 [>=N, ldw]; strides taken from tensors."""
-    assert A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16 and A.dim() == 2 and W.dim() == 2
+    """out = epilogue(A @ W[:N,:K].T + bias).  A bf16 [M, lda], W bf16 [>=N, ldw]; strides taken from tensors.
+    Both f32 (holding TF32-rounded values): the kind::tf32 contraction of the TF32 parity mode (operand_type 1)."""
+    assert A.dtype == W.dtype and A.dtype in (torch.bfloat16, torch.float32) and A.dim() == 2 and W.dim() == 2
     assert A.stride(1) == 1 and W.stride(1) == 1 and out.stride(-1) == 1
     M = A.shape[0]
     K = A.shape[1] if K is None else K
@@ -210,7 +211,8 @@ def gemm(A: torch.Tensor, W: torch.Tensor, bias, out: torch.Tensor, epilogue: in
     out2 = out.view(-1, out.shape[-1]) if out.dim() != 2 else out
     args = GemmArgs(M=M, N=N, K=K, A=ptr(A), lda=A.stride(0), W=ptr(W), ldw=W.stride(0), bias=ptr(bias),
                     out=ptr(out2), ldo=out2.stride(0), epilogue=epilogue, resid=ptr(resid), gate=ptr(gate),
-                    gate_stride=gate_stride, rows_per_gate=rows_per_gate, backend=backend)
+                    gate_stride=gate_stride, rows_per_gate=rows_per_gate, backend=backend,
+                    operand_type=1 if A.dtype == torch.float32 else 0)
     with torch.cuda.device(A.device), _launch("gemm", 1, (M, N, K, epilogue)):
         check(load().ldt_gemm_bf16(C.byref(args), stream_ptr()), "ldt_gemm_bf16")
     return out
@@ -291,6 +293,34 @@ def attention_nk32(B: int, H: int, Nq: int, dh: int, q, ldq: int, k, v, ldkv: in
     with torch.cuda.device(o.device), _launch("attention"):
         check(load().ldt_attention_nk32(B, H, Nq, dh, ptr(q), ldq, ptr(k), ptr(v), ldkv, ptr(o), stream_ptr()),
               "ldt_attention_nk32")
+
+
+def round_pad_tf32(x: torch.Tensor, ld_out: int | None = None, out: torch.Tensor | None = None, silu: bool = False) -> torch.Tensor:
+    """f32 [rows, cols] -> f32 [rows, ld_out]: (SiLU, then) rounded to the nearest TF32 value, columns zero-padded."""
+    _req(x, torch.float32, "x")
+    rows, cols = x.shape
+    ld_out = cols if ld_out is None else ld_out
+    if out is None:
+        out = torch.empty((rows, ld_out), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device), _launch("round_pad_tf32"):
+        check(load().ldt_round_pad_tf32(rows, cols, ptr(x), x.stride(0), ptr(out), out.stride(0), int(silu), stream_ptr()),
+              "ldt_round_pad_tf32")
+    return out
+
+
+def layernorm_mod_f32(x: torch.Tensor, out: torch.Tensor, *, shift=None, scale=None, mod_stride: int = 0,
+                      rows_per_mod: int = 1, weight=None, bias=None, eps: float = 1e-6) -> torch.Tensor:
+    rows, Cc = x.shape
+    with torch.cuda.device(x.device), _launch("layernorm"):
+        check(load().ldt_layernorm_mod_f32(rows, Cc, ptr(x), ptr(shift), ptr(scale), mod_stride, rows_per_mod,
+                                           ptr(weight), ptr(bias), eps, ptr(out), stream_ptr()), "ldt_layernorm_mod_f32")
+    return out
+
+
+def attention_nk32_f32(B: int, H: int, Nq: int, dh: int, q, ldq: int, k, v, ldkv: int, o) -> None:
+    with torch.cuda.device(o.device), _launch("attention"):
+        check(load().ldt_attention_nk32_f32(B, H, Nq, dh, ptr(q), ldq, ptr(k), ptr(v), ldkv, ptr(o), stream_ptr()),
+              "ldt_attention_nk32_f32")
 
 
 def set_attention_backend(backend: int) -> None:

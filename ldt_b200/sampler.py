@@ -84,7 +84,11 @@ def modulation_table(score, P, timesteps: torch.Tensor, chunk: int = 256) -> tor
         sc = torch.empty((R, score.t_dim), dtype=torch.bfloat16, device=dev)
         scratch = torch.empty((R, score.t_dim + 2 * half), dtype=torch.float32, device=dev)
         ops.time_embedding(timesteps[s:e].contiguous(), P["freq"], w0, b0, w1, b1, None, c, sc, scratch)
-        ops.gemm(sc, P["w_ada"], P["b_ada"], table[s:e], ops.EPI_BIAS_F32)
+        if score.precision == "tf32":
+            Q = score.packed_tf32()
+            ops.gemm(ops.round_pad_tf32(c, silu=True), Q["w_ada"], Q["b_ada"], table[s:e], ops.EPI_BIAS_F32)
+        else:
+            ops.gemm(sc, P["w_ada"], P["b_ada"], table[s:e], ops.EPI_BIAS_F32)
     return table
 
 
@@ -227,7 +231,9 @@ def fused_sample_loop(score, sde, x0, N, predictor, time_eps, probability_flow, 
     device = x0.device
     B = x0.shape[0]
     per_sample_c, cross = extra is not None, cond_tokens is not None
-    key = (B, N, predictor, float(time_eps), bool(probability_flow), device, use_graph,
+    if score.precision == "tf32" and (per_sample_c or cross):
+        raise NotImplementedError("precision='tf32' samples conditionally through the per-step path only")
+    key = (score.precision, B, N, predictor, float(time_eps), bool(probability_flow), device, use_graph,
            per_sample_c, cross, corrector_steps, float(snr), score._fingerprint())
     sg = _graph_cache.get(key)
     # the plan belongs to these two objects: weak references, not id() (an id can be reused after garbage collection)

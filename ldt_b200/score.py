@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._lib import EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_GATE_RESID_F32
+from ._lib import EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_BIAS_GELU_F32, EPI_GATE_RESID_F32
 
 TOKENS_PAD = 64  # K padding granule of the GEMM core
 
@@ -183,6 +183,11 @@ class Score(nn.Module):
         # boost clocks, but at the board's power cap the whole token pass measures the same (5.34 vs 5.31 ms, interleaved
         # A/B, scripts/exp_step_ab.py): the default stays with the two launches, which wait on nothing.
         self.fused_mlp = False
+        # "bf16" (product path: bf16 operands, fp32 accumulate) or "tf32": the parity mode -- fp32 activations end to end
+        # and kind::tf32 contractions, the precision of the reference's own GPU arithmetic (cuDNN TF32 convolutions).
+        # ~4x tighter against the fp32 reference than bf16 (tests/test_gpu_model.py), about half the speed; plain (non-UNet)
+        # score nets with head dim 32 or 64.
+        self.precision = "bf16"
 
     # ------------------------------------------------------------------------------------------
     # weight packing (fp32 parameters -> bf16 K-major GEMM operands), invalidated when any parameter's
@@ -204,6 +209,101 @@ class Score(nn.Module):
         self._packed = None
         self._packed_key = None
         self._generation = getattr(self, "_generation", 0) + 1
+
+    def packed_tf32(self):
+        """fp32 copies of the contraction weights rounded to TF32 (K padded to 32), for precision = "tf32"."""
+        key = self._fingerprint()
+        if getattr(self, "_packed32", None) is not None and key == self._packed32_key:
+            return self._packed32
+        if self.unet:
+            raise NotImplementedError("ldt_b200.Score: precision='tf32' covers the plain (non-UNet) score net")
+
+        def rw(w):   # [out, in, 1] or [out, in] parameter -> rounded f32 [out, pad32(in)]
+            w2 = w.detach().reshape(w.shape[0], -1).float().contiguous()
+            return ops.round_pad_tf32(w2, _pad_to(w2.shape[1], 32))
+
+        def fb(b):
+            return b.detach().float().contiguous()
+
+        Q = {"blocks": []}
+        with torch.no_grad():
+            Q["w_in"], Q["b_in"] = rw(self.ln_in.weight), fb(self.ln_in.bias)
+            ada_w, ada_b = [], []
+            for blk in self.Transformer:
+                wq = torch.cat([blk.fc_q.weight.detach().reshape(self.hidden_size, -1),
+                                blk.fc_kv.weight.detach().reshape(2 * self.hidden_size, -1)], dim=0)
+                Q["blocks"].append({
+                    "w_qkv": rw(wq), "b_qkv": torch.cat([blk.fc_q.bias.detach(), blk.fc_kv.bias.detach()]).float().contiguous(),
+                    "w_o": rw(blk.fc_o.weight), "b_o": fb(blk.fc_o.bias),
+                    "w_fc1": rw(blk.mlp.fc[0][0].weight), "b_fc1": fb(blk.mlp.fc[0][0].bias),
+                    "w_fc2": rw(blk.mlp.out.weight), "b_fc2": fb(blk.mlp.out.bias)})
+                ada_w.append(blk.adaLN[1].weight.detach())
+                ada_b.append(blk.adaLN[1].bias.detach())
+            ada_w.append(self.ln_out.adaLN[1].weight.detach())
+            ada_b.append(self.ln_out.adaLN[1].bias.detach())
+            Q["w_ada"], Q["b_ada"] = rw(torch.cat(ada_w, dim=0)), torch.cat(ada_b).float().contiguous()
+            Q["w_out"], Q["b_out"] = rw(self.ln_out.ln.weight), fb(self.ln_out.ln.bias)
+        self._packed32, self._packed32_key = Q, key
+        return Q
+
+    def _workspace_tf32(self, M, device):
+        if not hasattr(self, "_ws32"):
+            self._ws32 = {}
+        ws = self._ws32.get(M)
+        if ws is None or ws["h"].device != device:
+            Hd, f32 = self.hidden_size, torch.float32
+            ws = {"xa": torch.zeros((M, _pad_to(self.z_dim, 32)), dtype=f32, device=device),
+                  "a": torch.empty((M, Hd), dtype=f32, device=device), "qkv": torch.empty((M, 3 * Hd), dtype=f32, device=device),
+                  "att": torch.empty((M, Hd), dtype=f32, device=device), "hid": torch.empty((M, 4 * Hd), dtype=f32, device=device),
+                  "h": torch.empty((M, Hd), dtype=f32, device=device)}
+            self._ws32[M] = ws
+        return ws
+
+    def _run_tokens_tf32(self, x_tokens, mod, mod_stride, out, cond_tokens=None):
+        """run_tokens with fp32 activations and kind::tf32 contractions (precision = "tf32")."""
+        Q = self.packed_tf32()
+        Hd, T = self.hidden_size, self.z_scale
+        M = x_tokens.shape[0]
+        B = M // T
+        heads, dh = self.num_heads, Hd // self.num_heads
+        if dh not in (32, 64):
+            raise NotImplementedError("ldt_b200.Score: precision='tf32' needs head dim 32 or 64")
+        ws = self._workspace_tf32(M, x_tokens.device)
+        mp = mod.data_ptr()
+
+        def mview(off):
+            return _PtrView(mp + 4 * off)
+
+        h, a, qkv, att, hid = ws["h"], ws["a"], ws["qkv"], ws["att"], ws["hid"]
+        ops.round_pad_tf32(x_tokens, ws["xa"].shape[1], out=ws["xa"])
+        ops.gemm(ws["xa"], Q["w_in"], Q["b_in"], h, EPI_BIAS_F32)
+        kvc = None
+        if cond_tokens is not None:   # condition tokens [B, hidden, T] -> token-major, rounded: K/V source of the even blocks
+            kvc = ops.round_pad_tf32(cond_tokens.transpose(1, 2).contiguous().view(M, Hd).float())
+            kv = torch.empty((M, 2 * Hd), dtype=torch.float32, device=h.device)
+        k = _PtrView(qkv.data_ptr() + 4 * Hd)
+        v = _PtrView(qkv.data_ptr() + 8 * Hd)
+        for i, W in enumerate(Q["blocks"]):
+            base = i * 6 * Hd
+            ops.layernorm_mod_f32(h, a, shift=mview(base), scale=mview(base + Hd), mod_stride=mod_stride, rows_per_mod=T)
+            if kvc is not None and i % 2 == 0:
+                ops.gemm(a, W["w_qkv"], W["b_qkv"], qkv, EPI_BIAS_F32, N=Hd)
+                ops.gemm(kvc, W["w_qkv"][Hd:], W["b_qkv"][Hd:], kv, EPI_BIAS_F32)
+                ops.attention_nk32_f32(B, heads, T, dh, qkv, 3 * Hd, kv, _PtrView(kv.data_ptr() + 4 * Hd), 2 * Hd, att)
+            else:
+                ops.gemm(a, W["w_qkv"], W["b_qkv"], qkv, EPI_BIAS_F32)
+                ops.attention_nk32_f32(B, heads, T, dh, qkv, 3 * Hd, k, v, 3 * Hd, att)
+            ops.gemm(att, W["w_o"], W["b_o"], h, EPI_GATE_RESID_F32, resid=h, gate=mview(base + 2 * Hd),
+                     gate_stride=mod_stride, rows_per_gate=T)
+            ops.layernorm_mod_f32(h, a, shift=mview(base + 3 * Hd), scale=mview(base + 4 * Hd), mod_stride=mod_stride,
+                                  rows_per_mod=T)
+            ops.gemm(a, W["w_fc1"], W["b_fc1"], hid, EPI_BIAS_GELU_F32)
+            ops.gemm(hid, W["w_fc2"], W["b_fc2"], h, EPI_GATE_RESID_F32, resid=h, gate=mview(base + 5 * Hd),
+                     gate_stride=mod_stride, rows_per_gate=T)
+        base = self.num_blocks * 6 * Hd
+        ops.layernorm_mod_f32(h, a, shift=mview(base), scale=mview(base + Hd), mod_stride=mod_stride, rows_per_mod=T)
+        ops.gemm(a, Q["w_out"], Q["b_out"], out, EPI_BIAS_F32, N=self.z_dim)
+        return out
 
     def packed(self):
         key = self._fingerprint()
@@ -294,6 +394,10 @@ class Score(nn.Module):
         """
         w0, b0, w1, b1 = P["te"]
         ops.time_embedding(t, P["freq"], w0, b0, w1, b1, extra, ws.c, ws.sc, ws.scratch)
+        if self.precision == "tf32":
+            Q = self.packed_tf32()
+            ops.gemm(ops.round_pad_tf32(ws.c, silu=True), Q["w_ada"], Q["b_ada"], ws.mod, EPI_BIAS_F32)
+            return ws.mod
         ops.gemm(ws.sc, P["w_ada"], P["b_ada"], ws.mod, EPI_BIAS_F32)
         return ws.mod
 
@@ -311,6 +415,10 @@ class Score(nn.Module):
     def run_tokens(self, P, ws, x_tokens, mod, mod_stride, out, kv_cond=None):
         """The per-step token path: x_tokens f32 [M, z_dim] -> out f32 [M, z_dim].  ``mod`` holds the AdaLN
         rows (one row broadcast when mod_stride == 0, else one per sample)."""
+        if self.precision not in ("bf16", "tf32"):
+            raise ValueError(f"ldt_b200.Score.precision must be 'bf16' or 'tf32', got {self.precision!r}")
+        if self.precision == "tf32":
+            return self._run_tokens_tf32(x_tokens, mod, mod_stride, out, cond_tokens=getattr(self, "_cond_tokens32", None))
         if self.unet:
             return self._run_tokens_unet(P, ws, x_tokens, mod, mod_stride, out, kv_cond)
         Hd, T = self.hidden_size, self.z_scale
@@ -446,14 +554,20 @@ class Score(nn.Module):
             if label is None and torch.is_tensor(cond_vec):
                 extra = cond_vec.float().expand(B, self.t_dim).contiguous()  # c = t_emb + condition[1]  (score.py:135)
             if torch.is_tensor(cond_tokens):
-                kv_cond = self.project_condition_tokens(P, cond_tokens)
+                if self.precision == "tf32":
+                    self._cond_tokens32 = cond_tokens
+                else:
+                    kv_cond = self.project_condition_tokens(P, cond_tokens)
         ws = self._workspace(B, B, x.device)
         with torch.no_grad():
             tt = t.to(device=x.device, dtype=torch.float32).contiguous()
             mod = self.modulation(P, ws, tt, extra)
             out = torch.empty((B, self.z_scale, self.z_dim), dtype=torch.float32, device=x.device)
             xt = x.detach().float().contiguous().view(B * self.z_scale, self.z_dim)
-            self.run_tokens(P, ws, xt, mod, ws.mod_len, out.view(B * self.z_scale, self.z_dim), kv_cond)
+            try:
+                self.run_tokens(P, ws, xt, mod, ws.mod_len, out.view(B * self.z_scale, self.z_dim), kv_cond)
+            finally:
+                self._cond_tokens32 = None
         return out
 
 

@@ -231,6 +231,9 @@ class DiffusionVPSDE:
             from .sampler import fused_sample_loop, find_score_module  # late import (sampler imports Score)
             fusable = (predictor is not None and (corrector is None or corrector == "ancestral")
                        and not isinstance(condition, dict))
+            owner_model = getattr(getattr(score_fn, "__self__", None), "model", None)
+            if getattr(owner_model, "precision", "bf16") == "tf32" and (condition is not None or label is not None):
+                fusable = False   # the TF32 parity mode samples conditionally through the per-step path
             score_mod = None
             if fusable:   # one real call of score_fn must reproduce what the fused step hard-wires (sampler.py)
                 probe_t = torch.ones((num_samples,), device=device) * torch.linspace(1.0, time_eps, N, device=device)[0]

@@ -35,6 +35,13 @@ def bf16_round(x):
     return x.to(torch.bfloat16).to(x.dtype)
 
 
+def tf32_round(x):
+    """fp32 -> nearest TF32 value (10 mantissa bits, ties away from zero: PTX cvt.rna.tf32.f32), kept in fp32.  Tests set
+    QUANT = tf32_round to emulate where the TF32 parity mode of the B200 path rounds its contraction operands."""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 def _q(x):
     return x if QUANT is None else QUANT(x)
 

@@ -331,6 +331,47 @@ def test_gemm_all_epilogues(dev, backend, M, N, K):
             assert torch.all(out[:, N:].float() == 7.0), "wrote outside the N columns"
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 256, 32), (512, 1024, 1024), (8192, 1024, 4096), (300, 120, 128), (64, 3072, 1024),
+                                   (2048, 4096, 1024)])
+def test_gemm_tf32_operands(dev, M, N, K):
+    """operand_type 1: fp32 operands through the CTA-pair pipeline as kind::tf32 (the TF32 parity mode).  (1) small-integer
+    inputs: exact, bit-equal to fp64 -- catches tensor-map / descriptor / K-advance mistakes of the f32 layout; (2) TF32-
+    rounded random inputs: every product is exact in fp32, only the summation order differs from torch's fp32 matmul
+    (run with allow_tf32 off); (3) the three epilogues available to f32 operands."""
+    from ldt_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randint(-4, 5, (M, K), generator=g).float().to(dev)
+    W = torch.randint(-4, 5, (N, K), generator=g).float().to(dev)
+    bias = torch.randint(-8, 9, (N,), generator=g).float().to(dev)
+    ldo = (N + 7) // 8 * 8
+    out = torch.full((M, ldo), 7.0, device=dev)
+    ops.gemm(A, W, bias, out, 0, N=N, K=K)
+    assert torch.equal(out[:, :N], (A.double() @ W.double().t() + bias.double()).float())
+    if ldo > N:
+        assert torch.all(out[:, N:] == 7.0)
+    A = O.tf32_round(torch.randn((M, K), generator=g) * 0.5).to(dev)
+    W = O.tf32_round(torch.randn((N, K), generator=g) / K ** 0.5).to(dev)
+    bias = torch.randn((N,), generator=g).to(dev)
+    acc = (A.double() @ W.double().t() + bias.double())
+    out = torch.empty((M, ldo), device=dev)
+    ops.gemm(A, W, bias, out, 0, N=N, K=K)
+    assert rel_rms_err(out[:, :N], acc) < 5e-5, rel_rms_err(out[:, :N], acc)   # tensor-core fp32 accumulation order / alignment
+    ops.gemm(A, W, bias, out, 4, N=N, K=K)     # tf32_round(gelu_erf(acc + bias))
+    ref = O.tf32_round(torch.nn.functional.gelu(acc.float().cpu())).to(dev)
+    # one TF32 ulp (2^-10 relative) where the fp32 sum lands on the other side of a rounding boundary, plus the fp32
+    # accumulation noise of the pre-activation
+    assert torch.allclose(out[:, :N], ref, rtol=2.0 ** -9, atol=2e-5), (out[:, :N] - ref).abs().max()
+    rpg = 32
+    resid = torch.randn((M, ldo), generator=g).to(dev)
+    gate = torch.randn(((M + rpg - 1) // rpg, N), generator=g).to(dev)
+    out = resid.clone()
+    ops.gemm(A, W, bias, out, 3, N=N, K=K, resid=out, gate=gate, gate_stride=N, rows_per_gate=rpg)
+    ref = resid[:, :N].double() + gate.double().repeat_interleave(rpg, 0)[:M] * acc
+    assert rel_rms_err(out[:, :N], ref) < 2e-4   # worst element over 8 M outputs; gate * acc scales the accumulation noise
+    with pytest.raises(RuntimeError):
+        ops.gemm(A, W, bias, torch.empty((M, ldo), dtype=torch.bfloat16, device=dev), 1, N=N, K=K)   # no bf16 epilogue for f32 operands
+
+
 def test_gemm_tcgen05_matches_cross_check_bitwise_on_exact_inputs(dev):
     """Small-integer inputs make every product and partial sum exact, so tcgen05, the SIMT cross-check and fp64
     must agree to the bit: catches descriptor / swizzle / K-advance mistakes that tolerance tests can hide."""

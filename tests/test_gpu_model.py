@@ -166,6 +166,73 @@ def test_score_block0_output_vs_reference_golden(dev, tag, cfg_fn, seed):
     assert rms_rel_err(h0, g["h_block0"]) < 1e-2, rms_rel_err(h0, g["h_block0"])   # one block: bf16 operand noise only
 
 
+# ------------------------------------------------------------------------------------------------
+# TF32 parity mode (Score.precision = "tf32"): fp32 activations, kind::tf32 contractions
+# ------------------------------------------------------------------------------------------------
+# Achieved on B200 (profiles/r02_tf32_parity.txt) against the fp32 reference golden: small net 8.5e-4 rms (bf16 mode
+# 7.6e-3), full 24-block net 3.25e-3 (bf16 mode 2.84e-2), configs[0] default-init trajectory 4.1e-4 (bf16 mode 3.3e-3):
+# 8-9x tighter, i.e. the 2^-11 vs 2^-8 operand rounding.  Bars at 2x the measured values.
+TOL_TF32_RMS_SMALL = 1.7e-3
+TOL_TF32_RMS_FULL = 6.5e-3
+
+
+def test_score_tf32_mode_vs_reference_golden(dev):
+    """The reference's GPU arithmetic is TF32 for every Conv1d (cuDNN, allow_tf32 default) -- this mode matches that
+    precision: same goldens as the bf16 tests, ~10x tighter bars.  Small net, full 24-block net, conditional call."""
+    for tag, cfg, seed, tol in (("small", small_score_cfg(), 11, TOL_TF32_RMS_SMALL),
+                                ("full", ns(airplane_config()).score, 12, TOL_TF32_RMS_FULL)):
+        g = golden(f"score_{tag}.npz")
+        model, sd = build_score(cfg, seed, dev)
+        with torch.no_grad():
+            bf16 = model(g["x"].to(dev), g["t"].to(dev))
+            model.precision = "tf32"
+            out = model(g["x"].to(dev), g["t"].to(dev))
+            again = model(g["x"].to(dev), g["t"].to(dev))
+        r, m, rb = rms_rel_err(out, g["params"]), rel_rms_err(out, g["params"]), rms_rel_err(bf16, g["params"])
+        print(f"\nscore_{tag}: tf32 mode rms {r:.3e} max/rms {m:.3e} vs fp32 reference   (bf16 mode rms {rb:.3e})")
+        assert torch.equal(out, again)
+        assert r < tol and r < 0.25 * rb, (tag, r, rb)
+        O.QUANT = O.tf32_round
+        try:
+            emu = O.score_forward(sd, cfg, g["x"], g["t"])
+        finally:
+            O.QUANT = None
+        print(f"score_{tag}: tf32 mode vs the oracle with TF32 operand rounding: rms {rms_rel_err(out, emu):.3e}")
+        assert rms_rel_err(out, emu) < tol, rms_rel_err(out, emu)
+        if tag == "small":
+            gc = golden("score_small_cond.npz")
+            with torch.no_grad():
+                oc = model(gc["x"].to(dev), gc["t"].to(dev), condition=(gc["pts_cond"].to(dev), gc["img_cond"].to(dev)))
+            assert rms_rel_err(oc, gc["params"]) < tol, rms_rel_err(oc, gc["params"])
+
+
+def test_tf32_mode_trajectory_and_fused_sampler(dev):
+    """configs[0] teacher-forced in the TF32 mode (default init, the reference's own trajectory), and the fused graph loop
+    in that mode == its stepwise path."""
+    from ldt_b200 import DiffusionVPSDE, Score
+    g = golden("trajectory_b16.npz")
+    c = ns(airplane_config())
+    torch.manual_seed(0)
+    model = Score(c.score).to(dev).eval()
+    model.precision = "tf32"
+    sde = DiffusionVPSDE(c.sde, device=dev)
+    _, ts = sde.step_coefficients("ancestral", c.sde.sample_N, c.sde.sample_time_eps, False, dev)
+    print()
+    for i in (0, 100, 999):
+        with torch.no_grad():
+            params = model(g[f"x_{i}"].to(dev), torch.ones(16, device=dev) * ts[i])
+        r, m = rms_rel_err(params, g[f"params_{i}"]), rel_rms_err(params, g[f"params_{i}"])
+        print(f"step {i}: tf32 mode params rms {r:.3e} max/rms {m:.3e} vs the reference (bf16 mode: 3.3e-3 / 1.5e-2)")
+        assert r < 8e-4 and m < 4e-3, (i, r, m)    # measured 4.1e-4 / 1.8e-3
+    tr = _Trainer(model, sde)
+    torch.manual_seed(3); torch.cuda.manual_seed(3)
+    fused = sde.sample_discrete(tr.score_fn, 4, 6, "ancestral", None, 1, (32, 120), 1e-6, False, True, 0.01, dev)
+    torch.manual_seed(3); torch.cuda.manual_seed(3)
+    generic = sde.sample_discrete(lambda t, x, label=None, condition=None: tr.score_fn(t, x), 4, 6, "ancestral", None, 1,
+                                  (32, 120), 1e-6, False, True, 0.01, dev)
+    assert rel_rms_err(fused, generic) < 1e-5, rel_rms_err(fused, generic)
+
+
 def test_score_vs_oracle_float64_on_ragged_batch(dev):
     """Batch 5 (M = 160 rows: not a multiple of the 128-row tile) against the float64 oracle."""
     cfg = small_score_cfg()
