@@ -23,14 +23,14 @@ for st in $STAGES; do
     benchref) run benchref 600 python bench.py --impl reference --steps 1 --warmup 0 ;;
     launches) run launches 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --sde-steps 2 --steps 1 --warmup 1 --no-cpu-baseline --no-gpu-eager --cd-clouds 16 --no-secondary ;;
     ncufull)
-      for k in ${NCU_KERNELS:-gemm_tc2_kernel qkv_attention_kernel layernorm_mod_kernel sde_step_kernel}; do
+      for k in ${NCU_KERNELS:-gemm_tc2_kernel qkv_attention_kernel layernorm_mod_kernel sde_step_kernel attention_tc_kernel}; do
         run ncu_$k 400 ncu --set full --clock-control none --import-source on -k regex:$k -s ${NCU_SKIP:-6} -c 2 -f -o gpurun_out/prof_$k \
           python bench.py --sde-steps 2 --steps 1 --warmup 1 --no-cpu-baseline --no-gpu-eager --cd-clouds 16 --no-secondary
       done ;;
     ncuemd) run ncu_emd 400 ncu --set full --clock-control none --import-source on -k regex:approx_match_kernel -c 1 -f -o gpurun_out/prof_approx_match_kernel \
           python bench.py --sde-steps 2 --steps 1 --warmup 1 --no-cpu-baseline --no-gpu-eager --cd-clouds 16 --emd-clouds 13 --completion-batch 8 ;;
-    ncucd) run ncu_pairwise_cd 400 ncu --set full --clock-control none --import-source on -k regex:pairwise_cd_kernel -c 1 -f -o gpurun_out/prof_pairwise_cd_kernel \
-          python bench.py --sde-steps 2 --steps 1 --warmup 1 --no-cpu-baseline --no-gpu-eager --cd-clouds 64 --no-secondary ;;
+    ncucd) run ncu_pairwise_cd 400 ncu --set full --clock-control none --import-source on -k regex:pairwise_cd_kernel -s 2 -c 1 -f -o gpurun_out/prof_pairwise_cd_kernel \
+          python bench.py --sde-steps 2 --steps 1 --warmup 1 --no-cpu-baseline --no-gpu-eager --cd-clouds 128 --no-secondary ;;
     *) echo "unknown stage $st" ;;
   esac
 done
