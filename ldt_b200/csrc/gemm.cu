@@ -799,6 +799,8 @@ static int launch_any(const ldt_gemm_args& a, const EpiParams& p, cudaStream_t s
       const double u256 = static_cast<double>(t256) / (((t256 + pairs - 1) / pairs) * pairs);
       const double u128 = static_cast<double>(t128) / (((t128 + pairs - 1) / pairs) * pairs);
       if (u128 > u256 + 0.1) return launch_tc2<128, EPI>(a, p, s);
+      if ((p.dbg_mode & 1024) && a.N == 1024 && a.K == 1024) return launch_tc2<128, EPI>(a, p, s);   // experiment: fc_o on 256 x 128 tiles
+      if ((p.dbg_mode & 2048) && a.N == 1024 && a.K == 4096) return launch_tc2<128, EPI>(a, p, s);   // experiment: fc2 on 256 x 128 tiles
       return launch_tc2<256, EPI>(a, p, s);
     }
     return launch_tc2<128, EPI>(a, p, s);
