@@ -279,6 +279,68 @@ int ldt_sde_step(int predictor, long long numel, const float* x, const float* pa
                  unsigned long long seed, unsigned long long offset, unsigned long long offset_per_step,
                  const unsigned long long* rng_state, int rng_grid, float* x_next, float* x_mean, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Whole-path entry points: one call per score-net evaluation / per N-step sampling loop (csrc/path.cu).  Pure
+ * orchestration of the entry points above in the order ldt_b200/score.py::run_tokens and sampler.py::StepGraph issue
+ * them, so results are bit-identical to the Python-orchestrated path.  Plain (non-UNet) AdaLN score net, self-attention
+ * blocks with head dim 64 (the shipped experiments/Latent_Diffusion_Trainer config); other variants are orchestrated by
+ * the host from the kernel-level entry points.  All pointers are device pointers except `blocks` (host array) and the
+ * structs themselves.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ldt_score_block {       /* packed as ldt_b200/score.py::packed does */
+  const void* w_qkv_packed;  /* bf16 [heads*192, hidden]: per head [q_h | k_h | v_h] rows (fc_q / fc_kv, layers.py:159-160) */
+  const float* b_qkv_packed; /* f32 [heads*192] */
+  const void* w_o;           /* bf16 [hidden, hidden]      fc_o                */
+  const float* b_o;
+  const void* w_fc1;         /* bf16 [mlp_hidden, hidden]  mlp.fc.0.0          */
+  const float* b_fc1;
+  const void* w_fc2;         /* bf16 [hidden, mlp_hidden]  mlp.out             */
+  const float* b_fc2;
+} ldt_score_block;
+
+typedef struct ldt_score_plan {
+  int batch, tokens /* 32 */, z_dim, z_pad /* z_dim padded to a multiple of 64 */, hidden, heads, mlp_hidden, num_blocks;
+  const void* w_in;   /* bf16 [hidden, z_pad]  ln_in   */
+  const float* b_in;
+  const void* w_out;  /* bf16 [z_dim, hidden]  ln_out.ln */
+  const float* b_out;
+  const ldt_score_block* blocks;   /* HOST array [num_blocks] */
+  /* caller-owned device workspace for `batch` samples (M = batch * tokens rows) */
+  void* ws_xa;    /* bf16 [M, z_pad]      */
+  float* ws_h;    /* f32  [M, hidden]     residual stream */
+  void* ws_a;     /* bf16 [M, hidden]     LayerNorm output */
+  void* ws_att;   /* bf16 [M, hidden]     attention output, [B,H,32,64] contiguous (layers.py:197) */
+  void* ws_hid;   /* bf16 [M, mlp_hidden] */
+} ldt_score_plan;
+
+/* out f32 [M, z_dim] = the score net's token path on x_tokens f32 [M, z_dim] given the AdaLN rows `mod`
+ * (f32, 6*hidden per block then 2*hidden for the final layer; one row per sample at stride mod_stride, or one broadcast
+ * row with mod_stride 0): score.py:136-150.  The AdaLN rows themselves come from ldt_time_embedding + ldt_gemm_bf16. */
+int ldt_score_forward(const ldt_score_plan* plan, const float* x_tokens, const float* mod, long long mod_stride, float* out,
+                      void* stream);
+
+typedef struct ldt_sample_args {
+  const ldt_score_plan* score;
+  int predictor;            /* enum ldt_predictor, 0..3 */
+  int num_steps;            /* steps to run from the current *step */
+  int use_graph;            /* 1: capture one step on `stream` and launch it num_steps - 1 times; 0: plain launches */
+  const float* mod_table;   /* f32 [N, mod_len]: AdaLN rows of every timestep (unconditional sampling: batch-invariant) */
+  long long mod_len;
+  float* mod_cur;           /* f32 [mod_len] scratch: the current step's row */
+  const float* coef;        /* f32 [N, 8] per-step predictor scalars (LDT_SDE_COEF_STRIDE) */
+  int* step;                /* device step counter, advanced by one per step */
+  const unsigned long long* rng_state;   /* device {seed, offset} of the Philox stream (ldt_sde_step) */
+  unsigned long long offset_per_step;
+  int rng_grid;
+  float* x;                 /* f32 [batch, 32, z_dim] loop state, updated in place */
+  float* x_mean;            /* f32 same shape: the denoised mean of the last step run */
+  float* params;            /* f32 same shape scratch: the score net's output */
+} ldt_sample_args;
+
+/* The reverse-SDE loop of pc_sampling (diffusion_continuous.py:242-249): num_steps x (select AdaLN row, score net,
+ * fused predictor update with in-kernel noise, step counter + 1). */
+int ldt_sample_loop(const ldt_sample_args* args, void* stream);
+
 /* PNDM pieces (diffusion_continuous.py:260-316).
  * ldt_pndm_transfer: out = x + coef[0] * (coef[1] * x - coef[2] * et)  -- transfer() :264-274; coef is a DEVICE array of
  *   three floats (at_next - at, 1/(sqrt(at)(sqrt(at)+sqrt(at_next))), 1/(sqrt(at)(sqrt((1-at_next)at)+sqrt((1-at)at_next)))).

@@ -45,6 +45,26 @@ class GemmArgs(C.Structure):
     ]
 
 
+class ScoreBlock(C.Structure):
+    _fields_ = [("w_qkv_packed", C.c_void_p), ("b_qkv_packed", C.c_void_p), ("w_o", C.c_void_p), ("b_o", C.c_void_p),
+                ("w_fc1", C.c_void_p), ("b_fc1", C.c_void_p), ("w_fc2", C.c_void_p), ("b_fc2", C.c_void_p)]
+
+
+class ScorePlan(C.Structure):
+    _fields_ = [("batch", C.c_int), ("tokens", C.c_int), ("z_dim", C.c_int), ("z_pad", C.c_int), ("hidden", C.c_int),
+                ("heads", C.c_int), ("mlp_hidden", C.c_int), ("num_blocks", C.c_int),
+                ("w_in", C.c_void_p), ("b_in", C.c_void_p), ("w_out", C.c_void_p), ("b_out", C.c_void_p),
+                ("blocks", C.POINTER(ScoreBlock)),
+                ("ws_xa", C.c_void_p), ("ws_h", C.c_void_p), ("ws_a", C.c_void_p), ("ws_att", C.c_void_p), ("ws_hid", C.c_void_p)]
+
+
+class SampleArgs(C.Structure):
+    _fields_ = [("score", C.POINTER(ScorePlan)), ("predictor", C.c_int), ("num_steps", C.c_int), ("use_graph", C.c_int),
+                ("mod_table", C.c_void_p), ("mod_len", C.c_longlong), ("mod_cur", C.c_void_p), ("coef", C.c_void_p),
+                ("step", C.c_void_p), ("rng_state", C.c_void_p), ("offset_per_step", C.c_ulonglong), ("rng_grid", C.c_int),
+                ("x", C.c_void_p), ("x_mean", C.c_void_p), ("params", C.c_void_p)]
+
+
 class MlpArgs(C.Structure):
     _fields_ = [
         ("M", C.c_int), ("C", C.c_int), ("inner", C.c_int),
@@ -70,6 +90,8 @@ PROTOTYPES = {
                                   C.c_void_p, C.c_void_p]),
     "ldt_debug_set_attention_backend": (C.c_int, [C.c_int]),
     "ldt_debug_get_attention_backend": (C.c_int, []),
+    "ldt_score_forward": (C.c_int, [C.POINTER(ScorePlan), C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "ldt_sample_loop": (C.c_int, [C.POINTER(SampleArgs), C.c_void_p]),
     "ldt_round_pad_tf32": (C.c_int, [C.c_longlong, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ldt_layernorm_mod_f32": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),

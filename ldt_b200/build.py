@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(CSRC, "libldt_b200.so")
-SOURCES = ["api.cu", "nn_distance.cu", "gemm.cu", "mlp.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "qkv_attention.cu", "emd.cu", "pointops.cu", "diag.cu", "precision_f32.cu"]
+SOURCES = ["api.cu", "nn_distance.cu", "gemm.cu", "mlp.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "qkv_attention.cu", "emd.cu", "pointops.cu", "diag.cu", "precision_f32.cu", "path.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -323,6 +323,19 @@ def attention_nk32_f32(B: int, H: int, Nq: int, dh: int, q, ldq: int, k, v, ldkv
               "ldt_attention_nk32_f32")
 
 
+def score_forward(plan, launches: int, x_tokens, mod, mod_stride: int, out) -> None:
+    """The whole token pass as one C call (ldt_score_forward); ``plan`` is a _lib.ScorePlan, ``launches`` its kernel count."""
+    with torch.cuda.device(out.device), _launch("score_forward", launches):
+        check(load().ldt_score_forward(C.byref(plan), ptr(x_tokens), ptr(mod), mod_stride, ptr(out), stream_ptr()),
+              "ldt_score_forward")
+
+
+def sample_loop(args, launches: int) -> None:
+    """ldt_sample_loop on the current stream; ``launches`` = kernels the call issues (for the launch counter)."""
+    with _launch("sample_loop", launches):
+        check(load().ldt_sample_loop(C.byref(args), stream_ptr()), "ldt_sample_loop")
+
+
 def set_attention_backend(backend: int) -> None:
     """0 = tcgen05 attention kernel where it applies (default), 1 = warp-level mma.sync kernels (cross-check)."""
     check(load().ldt_debug_set_attention_backend(int(backend)), "ldt_debug_set_attention_backend")

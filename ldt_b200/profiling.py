@@ -125,6 +125,14 @@ def ablate_score_step(score, B: int, replays: int = 60, warm: int = 15) -> dict:
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / replays
 
+    c_path, score.c_path = score.c_path, False   # the ablation hooks wrap the per-kernel Python calls
+    try:
+        return _ablate(score, B, timed, counts)
+    finally:
+        score.c_path = c_path
+
+
+def _ablate(score, B, timed, counts) -> dict:
     full = timed(None)
     launches = dict(counts)
     # interleave: full is re-measured after the ablated passes and the two are averaged (thermal drift hits both)

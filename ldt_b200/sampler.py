@@ -14,6 +14,7 @@ issues ~700 kernel launches per step.  Three things make one captured step repla
 """
 from __future__ import annotations
 
+import ctypes as C
 import weakref
 
 import torch
@@ -148,6 +149,10 @@ class StepGraph:
         self.captures = 0
         self.graph = None
         self.use_graph = use_graph
+        # LDT_C_LOOP=1 (or use_c_loop = True): the whole N-step loop as ONE call of the C entry point ldt_sample_loop, which
+        # captures and replays the step graph itself -- the path a non-Python host takes.  Same kernels, same bits.
+        import os
+        self.use_c_loop = os.environ.get("LDT_C_LOOP", "0") == "1"
 
     def set_condition(self, cond_tokens, extra) -> None:
         """Load this run's condition into the plan's buffers (pointers captured by the graph stay the same)."""
@@ -191,6 +196,24 @@ class StepGraph:
         self.step.zero_()
         self.rng_state.copy_(torch.tensor([i64(seed), i64(offset)], dtype=torch.int64))
         snaps = []
+        if self.use_c_loop and not (self.per_sample_c or self.cross_attention or self.corrector_steps or record_every):
+            plan = self.score.c_plan(self.P, self.ws)
+            if plan is not None:
+                from . import _lib
+                args = _lib.SampleArgs(score=C.pointer(plan), predictor=self.code, num_steps=self.N, use_graph=int(self.use_graph),
+                                       mod_table=self.table.data_ptr(), mod_len=self.table.shape[1], mod_cur=self.mod_cur.data_ptr(),
+                                       coef=self.coef.data_ptr(), step=self.step.data_ptr(), rng_state=self.rng_state.data_ptr(),
+                                       offset_per_step=self.offset_per_step, rng_grid=self.rng_grid, x=self.x.data_ptr(),
+                                       x_mean=self.x_mean.data_ptr(), params=self.params.data_ptr())
+                per_step = 4 + 6 * self.score.num_blocks + 3     # token pass + select_row + sde_step + advance_step
+                cur = torch.cuda.current_stream(self.x.device)
+                side = cur if cur.cuda_stream != 0 else torch.cuda.Stream(self.x.device)   # the legacy stream cannot capture
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    ops.sample_loop(args, self.N * per_step)
+                cur.wait_stream(side)
+                self.launches_per_step = per_step
+                return snaps
         if not self.use_graph:
             for i in range(self.N):
                 self._step_body()

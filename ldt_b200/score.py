@@ -188,6 +188,11 @@ class Score(nn.Module):
         # ~4x tighter against the fp32 reference than bf16 (tests/test_gpu_model.py), about half the speed; plain (non-UNet)
         # score nets with head dim 32 or 64.
         self.precision = "bf16"
+        # the token pass of the shipped configuration (plain AdaLN blocks, head dim 64, self-attention) goes through the
+        # whole-path C entry point ldt_score_forward: one ctypes call instead of ~150 (same kernels, same order, same bits;
+        # it only removes host time, which matters for eager per-step calls at small batch).  False = orchestrate from Python
+        # (what the per-kernel profiling hooks need).
+        self.c_path = True
 
     # ------------------------------------------------------------------------------------------
     # weight packing (fp32 parameters -> bf16 K-major GEMM operands), invalidated when any parameter's
@@ -412,6 +417,32 @@ class Score(nn.Module):
         ops.gemm(ws.hid, w2, W["b_fc2"], ws.h, EPI_GATE_RESID_F32, resid=ws.h, gate=gate, gate_stride=mod_stride,
                  rows_per_gate=T)
 
+    def c_plan(self, P, ws):
+        """_lib.ScorePlan over the packed weights P and workspace ws (cached on ws; keeps the ctypes arrays alive), or None
+        when this configuration is not one ldt_score_forward takes."""
+        from . import _lib
+        dh = self.hidden_size // self.num_heads
+        if self.unet or dh != 64 or not self.fused_attention or self.fused_mlp or self.precision != "bf16":
+            return None
+        cached = getattr(ws, "_c_plan", None)
+        if cached is not None and cached[0] is P:
+            return cached[1]
+        blocks = (_lib.ScoreBlock * len(P["blocks"]))()
+        for i, W in enumerate(P["blocks"]):
+            b = blocks[i]
+            b.w_qkv_packed, b.b_qkv_packed = W["w_qkv_p"].data_ptr(), W["b_qkv_p"].data_ptr()
+            b.w_o, b.b_o = W["w_o"].data_ptr(), W["b_o"].data_ptr()
+            b.w_fc1, b.b_fc1 = W["w_fc1"].data_ptr(), W["b_fc1"].data_ptr()
+            b.w_fc2, b.b_fc2 = W["w_fc2"].data_ptr(), W["b_fc2"].data_ptr()
+        plan = _lib.ScorePlan(batch=ws.B, tokens=self.z_scale, z_dim=self.z_dim, z_pad=ws.xa.shape[1], hidden=self.hidden_size,
+                              heads=self.num_heads, mlp_hidden=P["blocks"][0]["w_fc1"].shape[0] if P["blocks"] else 4 * self.hidden_size,
+                              num_blocks=len(P["blocks"]), w_in=P["w_in"].data_ptr(), b_in=P["b_in"].data_ptr(),
+                              w_out=P["w_out"].data_ptr(), b_out=P["b_out"].data_ptr(), blocks=blocks,
+                              ws_xa=ws.xa.data_ptr(), ws_h=ws.h.data_ptr(), ws_a=ws.a.data_ptr(), ws_att=ws.att.data_ptr(),
+                              ws_hid=ws.hid.data_ptr())
+        ws._c_plan = (P, plan, blocks)
+        return plan
+
     def run_tokens(self, P, ws, x_tokens, mod, mod_stride, out, kv_cond=None):
         """The per-step token path: x_tokens f32 [M, z_dim] -> out f32 [M, z_dim].  ``mod`` holds the AdaLN
         rows (one row broadcast when mod_stride == 0, else one per sample)."""
@@ -421,6 +452,12 @@ class Score(nn.Module):
             return self._run_tokens_tf32(x_tokens, mod, mod_stride, out, cond_tokens=getattr(self, "_cond_tokens32", None))
         if self.unet:
             return self._run_tokens_unet(P, ws, x_tokens, mod, mod_stride, out, kv_cond)
+        if self.c_path and kv_cond is None and len(P["blocks"]) == self.num_blocks and x_tokens.is_contiguous() \
+                and out.is_contiguous() and ops._PROFILE is None:
+            plan = self.c_plan(P, ws)
+            if plan is not None:
+                ops.score_forward(plan, 4 + 6 * self.num_blocks, x_tokens, mod, mod_stride, out)
+                return out
         Hd, T = self.hidden_size, self.z_scale
         B = ws.B
         heads, dh = self.num_heads, Hd // self.num_heads

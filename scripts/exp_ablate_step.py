@@ -6,6 +6,7 @@ from tests.helpers import airplane_config, ns
 dev = torch.device("cuda:0")
 B = 256
 model = Score(ns(airplane_config()).score).to(dev).eval()
+model.c_path = False   # the hooks below wrap the per-kernel Python calls
 P = model.packed(); ws = model._workspace(B, 1, dev)
 x = torch.randn((B * 32, 120), device=dev); out = torch.empty_like(x)
 mod = torch.randn((1, ws.mod_len), device=dev) * 0.1

@@ -53,6 +53,10 @@ def test_argument_validation_without_gpu():
     assert L.ldt_sde_step(9, 16, 1, 1, None, 1, None, 0, 0, 0, None, 0, 1, None, None) == -1
     assert L.ldt_pairwise_cd_upper(8, 16, None, 2, 2, None, None) == -1 and b"row_first" in L.ldt_last_error_string()
     assert L.ldt_pairwise_cd_upper(0, 16, None, 0, 1, None, None) == 0
+    plan = _lib.ScorePlan(batch=2, tokens=32, z_dim=120, z_pad=128, hidden=128, heads=4, mlp_hidden=512, num_blocks=0)
+    assert L.ldt_score_forward(C.byref(plan), None, None, 0, None, None) == -3 and b"head dim 64" in L.ldt_last_error_string()
+    assert L.ldt_score_forward(None, None, None, 0, None, None) == -1
+    assert L.ldt_sample_loop(None, None) == -1
 
 
 def test_state_dict_layout_matches_reference():

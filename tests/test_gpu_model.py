@@ -377,6 +377,38 @@ def test_fused_plan_is_captured_once_and_reused_across_generator_positions(dev):
     assert plan.captures == 1
 
 
+def test_whole_path_c_entry_points_equal_python_orchestration(dev):
+    """ldt_score_forward (one call per token pass) and ldt_sample_loop (one call per N-step loop, its own CUDA graph) issue
+    the same kernels in the same order as score.py::run_tokens / sampler.StepGraph: bit-identical results."""
+    from ldt_b200 import DiffusionVPSDE, sampler
+    cfg = small_score_cfg()
+    model, _ = build_score(cfg, 11, dev)
+    g = torch.Generator().manual_seed(2)
+    x, t = torch.randn((5, 32, 120), generator=g).to(dev), torch.rand((5,), generator=g).to(dev)
+    with torch.no_grad():
+        assert model.c_path and model.c_plan(model.packed(), model._workspace(5, 5, dev)) is not None
+        via_c = model(x, t)
+        model.c_path = False
+        via_py = model(x, t)
+        model.c_path = True
+    assert torch.equal(via_c, via_py)
+    sde = DiffusionVPSDE(ns(airplane_config()).sde, device=dev)
+    tr = _Trainer(model, sde)
+    outs = []
+    for c_loop in (False, True):
+        sampler._graph_cache.clear()
+        torch.manual_seed(3); torch.cuda.manual_seed(3)
+        x0 = torch.randn(4, 32, 120).to(dev)
+        gen = torch.cuda.default_generators[0]
+        sgp = sampler.StepGraph(model, sde, 4, 9, "ancestral", 1e-6, False, dev)
+        sgp.use_c_loop = c_loop
+        sgp.run(x0, gen.initial_seed(), gen.get_offset())
+        torch.cuda.synchronize()
+        outs.append((sgp.x.clone(), sgp.x_mean.clone(), int(sgp.step.item())))
+    assert outs[0][2] == outs[1][2] == 9
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_overridden_score_fn_is_probed_and_not_silently_replaced(dev):
     """A Trainer subclass whose score_fn is NOT (-params/sqrt(var), params) must get the generic per-step path (with a
     one-time warning), not the fused loop that hard-wires that formula (VERDICT r1 weak #9)."""
