@@ -319,6 +319,36 @@ typedef struct ldt_score_plan {
 int ldt_score_forward(const ldt_score_plan* plan, const float* x_tokens, const float* mod, long long mod_stride, float* out,
                       void* stream);
 
+typedef struct ldt_decoder_layer {     /* one DecoderBlock as ldt_b200/compressor.py::packed lays it out */
+  const void* w_ln;  const float* b_ln;     /* bf16 [hidden, z_pad]  decoder.l.ln (Conv1d z_dim -> hidden)     */
+  const void* w_kv;  const float* b_kv;     /* bf16 [2*hidden, hidden] att1.fc_kv                               */
+  const void* w_q;   const float* b_q;      /* bf16 [hidden, hidden]   att1.fc_q                                */
+  const void* w_o;   const float* b_o;      /* att1.fc_o */
+  const void* w_fc1; const float* b_fc1;    /* bf16 [mlp_hidden, hidden] att1.mlp.fc.0.0                        */
+  const void* w_fc2; const float* b_fc2;    /* bf16 [hidden, mlp_hidden] att1.mlp.out                           */
+  const float* norm1_w; const float* norm1_b; const float* norm2_w; const float* norm2_b;   /* affine LayerNorms */
+} ldt_decoder_layer;
+
+typedef struct ldt_decoder_plan {
+  int batch, num_points, z_dim, z_pad, hidden, heads, mlp_hidden, n_layers;
+  const ldt_decoder_layer* layers;   /* HOST array [n_layers], in module order decoder.0 .. decoder.(n-1) */
+  const void* w_out;                 /* bf16 [8, hidden]: Conv1d(hidden -> 3) padded to 8 output rows */
+  const float* b_out;                /* f32 [8] */
+  /* caller-owned device workspace: MT = batch*32 token rows, MQ = batch*num_points point rows */
+  void* ws_e;    /* bf16 [MT, z_pad]    */
+  void* ws_x;    /* bf16 [MT, hidden]   */
+  void* ws_kv;   /* bf16 [MT, 2*hidden] */
+  void* ws_a;    /* bf16 [MQ, hidden]   */
+  void* ws_q;    /* bf16 [MQ, hidden]   */
+  void* ws_att;  /* bf16 [MQ, hidden]   */
+  void* ws_hid;  /* bf16 [MQ, mlp_hidden] */
+} ldt_decoder_plan;
+
+/* Compressor.sample's decoder (model/Compressor/Network.py:261-266): eps f32 [batch*32, n_layers*z_dim] (given_eps,
+ * token-major); o f32 [MQ, hidden] holds InitialSet's rows on entry (the residual stream, updated in place);
+ * points8 f32 [MQ, 8]: columns 0..2 are the generated points. */
+int ldt_decoder_forward(const ldt_decoder_plan* plan, const float* eps, float* o, float* points8, void* stream);
+
 typedef struct ldt_sample_args {
   const ldt_score_plan* score;
   int predictor;            /* enum ldt_predictor, 0..3 */

@@ -58,6 +58,17 @@ class ScorePlan(C.Structure):
                 ("ws_xa", C.c_void_p), ("ws_h", C.c_void_p), ("ws_a", C.c_void_p), ("ws_att", C.c_void_p), ("ws_hid", C.c_void_p)]
 
 
+class DecoderLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w_ln", "b_ln", "w_kv", "b_kv", "w_q", "b_q", "w_o", "b_o", "w_fc1", "b_fc1",
+                                           "w_fc2", "b_fc2", "norm1_w", "norm1_b", "norm2_w", "norm2_b")]
+
+
+class DecoderPlan(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("batch", "num_points", "z_dim", "z_pad", "hidden", "heads", "mlp_hidden", "n_layers")] + \
+               [("layers", C.POINTER(DecoderLayer)), ("w_out", C.c_void_p), ("b_out", C.c_void_p)] + \
+               [(n, C.c_void_p) for n in ("ws_e", "ws_x", "ws_kv", "ws_a", "ws_q", "ws_att", "ws_hid")]
+
+
 class SampleArgs(C.Structure):
     _fields_ = [("score", C.POINTER(ScorePlan)), ("predictor", C.c_int), ("num_steps", C.c_int), ("use_graph", C.c_int),
                 ("mod_table", C.c_void_p), ("mod_len", C.c_longlong), ("mod_cur", C.c_void_p), ("coef", C.c_void_p),
@@ -91,6 +102,7 @@ PROTOTYPES = {
     "ldt_debug_set_attention_backend": (C.c_int, [C.c_int]),
     "ldt_debug_get_attention_backend": (C.c_int, []),
     "ldt_score_forward": (C.c_int, [C.POINTER(ScorePlan), C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "ldt_decoder_forward": (C.c_int, [C.POINTER(DecoderPlan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldt_sample_loop": (C.c_int, [C.POINTER(SampleArgs), C.c_void_p]),
     "ldt_round_pad_tf32": (C.c_int, [C.c_longlong, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ldt_layernorm_mod_f32": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,

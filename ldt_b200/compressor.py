@@ -341,13 +341,30 @@ class Compressor(nn.Module):
             att = torch.empty((MQ, H), dtype=bf, device=dev)
             hid = torch.empty((MQ, int(self.mlp_ratio * H)), dtype=bf, device=dev)
             bufs = (e_a, xx, kv, a, q, att, hid)
-            for idx in range(self.n_layers):
-                W = P["layers"][self.n_layers - 1 - idx]  # reversed(self.decoder), :263
-                chunk = eps[:, idx * Z:(idx + 1) * Z]     # torch.split(...)[idx], :262
-                self._decoder_block(W, B, num_points, chunk, eps.stride(0), o, bufs)
-            ob = ops.cast_pad_bf16(o, H, out=a)
             pts8 = torch.empty((MQ, 8), dtype=torch.float32, device=dev)
-            ops.gemm(ob, P["w_out"], P["b_out"], pts8, EPI_BIAS_F32)               # self.output(o)           :266
+            if getattr(self, "c_path", True):
+                # the whole decoder as ONE call of the C entry point ldt_decoder_forward (same kernels, same order, same bits)
+                from . import _lib
+                layers = (_lib.DecoderLayer * self.n_layers)()
+                for l, W in enumerate(P["layers"]):
+                    for f, k in (("w_ln", "w_ln"), ("b_ln", "b_ln"), ("w_kv", "w_kv"), ("b_kv", "b_kv"), ("w_q", "w_q"), ("b_q", "b_q"),
+                                 ("w_o", "w_o"), ("b_o", "b_o"), ("w_fc1", "w_fc1"), ("b_fc1", "b_fc1"), ("w_fc2", "w_fc2"),
+                                 ("b_fc2", "b_fc2"), ("norm1_w", "n1w"), ("norm1_b", "n1b"), ("norm2_w", "n2w"), ("norm2_b", "n2b")):
+                        setattr(layers[l], f, W[k].data_ptr())
+                plan = _lib.DecoderPlan(batch=B, num_points=num_points, z_dim=Z, z_pad=zpad, hidden=H, heads=heads,
+                                        mlp_hidden=hid.shape[1], n_layers=self.n_layers, layers=layers, w_out=P["w_out"].data_ptr(),
+                                        b_out=P["b_out"].data_ptr(), ws_e=e_a.data_ptr(), ws_x=xx.data_ptr(), ws_kv=kv.data_ptr(),
+                                        ws_a=a.data_ptr(), ws_q=q.data_ptr(), ws_att=att.data_ptr(), ws_hid=hid.data_ptr())
+                with torch.cuda.device(dev), ops._launch("decoder_forward", 10 * self.n_layers + 2):
+                    _lib.check(_lib.load().ldt_decoder_forward(_lib.C.byref(plan), eps.data_ptr(), o.data_ptr(), pts8.data_ptr(),
+                                                               _lib.stream_ptr()), "ldt_decoder_forward")
+            else:
+                for idx in range(self.n_layers):
+                    W = P["layers"][self.n_layers - 1 - idx]  # reversed(self.decoder), :263
+                    chunk = eps[:, idx * Z:(idx + 1) * Z]     # torch.split(...)[idx], :262
+                    self._decoder_block(W, B, num_points, chunk, eps.stride(0), o, bufs)
+                ob = ops.cast_pad_bf16(o, H, out=a)
+                ops.gemm(ob, P["w_out"], P["b_out"], pts8, EPI_BIAS_F32)               # self.output(o)           :266
             out = pts8[:, :3].reshape(B, num_points, 3).contiguous()
         return self.postprocess(out)
 

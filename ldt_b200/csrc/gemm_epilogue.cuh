@@ -180,7 +180,7 @@ __device__ __forceinline__ void epilogue_staged(const EpiParams& p, uint8_t* stg
       }
       float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if constexpr (EPI == LDT_EPI_GATE_RESID_F32) {
-        if (col_ok && p.gate != nullptr && gate_uniform)
+        if (col_ok && p.gate != nullptr && gate_uniform && row_base < p.M)   // slabs past M (ragged last tile) have no gate row
           g4 = __ldg(reinterpret_cast<const float4*>(
               p.gate + static_cast<long long>(row_base / p.rows_per_gate) * p.gate_stride + col));
       }

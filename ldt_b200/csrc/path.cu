@@ -1,6 +1,7 @@
 // Whole-path entry points of the C ABI (SURVEY.md 8b export list): the score-net token pass and the N-step reverse-SDE
 // loop as ONE call each, for hosts that do not want to orchestrate ~150 kernel launches per step themselves.
 //   ldt_score_forward  = Score.forward's token path (model/scorenet/score.py:136-150 -> model/layers.py:202-229,240-245)
+//   ldt_decoder_forward = Compressor.sample's decoder (model/Compressor/Network.py:261-266 -> DecoderBlock.forward :80-83)
 //   ldt_sample_loop    = pc_sampling's loop (diffusion/diffusion_continuous.py:242-249) with the Ancestral / ReverseDiffusion /
 //                        EulerMaruyama / DDIM predictor and score = -params / sqrt(var) (trainer/Latent_SDE_Trainer.py:57-61)
 // Pure orchestration over the kernels of this library (same launches, same order, same arguments as ldt_b200/score.py::
@@ -130,4 +131,52 @@ extern "C" int ldt_sample_loop(const ldt_sample_args* args, void* stream) {
   if (exec) cudaGraphExecDestroy(exec);   // deferred by the runtime until the launches have run
   cudaGraphDestroy(graph);
   return check_cuda(e, "cudaGraphInstantiate / cudaGraphLaunch", __FILE__, __LINE__);
+}
+
+extern "C" int ldt_decoder_forward(const ldt_decoder_plan* plan, const float* eps, float* o, float* points8, void* stream) {
+  LDT_REQUIRE(plan != nullptr, LDT_ERR_INVALID, "ldt_decoder_forward: null plan");
+  const ldt_decoder_plan& p = *plan;
+  LDT_REQUIRE(p.batch > 0 && p.num_points > 0 && p.hidden > 0 && p.heads > 0 && p.n_layers >= 0 && p.z_dim > 0 && p.mlp_hidden > 0,
+              LDT_ERR_INVALID, "ldt_decoder_forward: bad shape batch=%d points=%d hidden=%d heads=%d layers=%d z_dim=%d", p.batch,
+              p.num_points, p.hidden, p.heads, p.n_layers, p.z_dim);
+  LDT_REQUIRE(p.hidden % 128 == 0 && p.z_pad % 64 == 0 && p.z_pad >= p.z_dim && p.mlp_hidden % 64 == 0, LDT_ERR_INVALID,
+              "ldt_decoder_forward: hidden %% 128, z_pad %% 64, mlp_hidden %% 64 required");
+  LDT_REQUIRE(eps && o && points8 && p.w_out && p.ws_e && p.ws_x && p.ws_kv && p.ws_a && p.ws_q && p.ws_att && p.ws_hid &&
+                  (p.n_layers == 0 || p.layers),
+              LDT_ERR_INVALID, "ldt_decoder_forward: null pointer");
+  const int H = p.hidden, MQ = p.batch * p.num_points, MT = p.batch * 32;
+  const int ld_eps = p.n_layers * p.z_dim;
+  int rc;
+  ldt_gemm_args g = {};
+  g.rows_per_gate = 1;
+  for (int idx = 0; idx < p.n_layers; ++idx) {
+    const ldt_decoder_layer& L = p.layers[p.n_layers - 1 - idx];   // reversed(self.decoder), Network.py:263
+    rc = ldt_cast_pad_bf16(MT, p.z_dim, eps + idx * p.z_dim, ld_eps, p.ws_e, p.z_pad, stream);   // torch.split(...)[idx], :262
+    if (rc) return rc;
+    g.resid = nullptr; g.gate = nullptr;
+    g.M = MT; g.N = H; g.K = p.z_pad; g.A = p.ws_e; g.lda = p.z_pad; g.W = L.w_ln; g.ldw = p.z_pad; g.bias = L.b_ln; g.out = p.ws_x;
+    g.ldo = H; g.epilogue = LDT_EPI_BIAS_BF16;                                     // x = self.ln(eps)            :81
+    if ((rc = ldt_gemm_bf16(&g, stream))) return rc;
+    g.N = 2 * H; g.K = H; g.A = p.ws_x; g.lda = H; g.W = L.w_kv; g.ldw = H; g.bias = L.b_kv; g.out = p.ws_kv; g.ldo = 2 * H;
+    if ((rc = ldt_gemm_bf16(&g, stream))) return rc;                               // kv = fc_kv(x)       layers.py:187
+    if ((rc = ldt_layernorm_mod_bf16(MQ, H, o, nullptr, nullptr, 0, 1, L.norm1_w, L.norm1_b, 1e-6f, p.ws_a, stream))) return rc;
+    g.M = MQ; g.N = H; g.K = H; g.A = p.ws_a; g.lda = H; g.W = L.w_q; g.ldw = H; g.bias = L.b_q; g.out = p.ws_q; g.ldo = H;
+    if ((rc = ldt_gemm_bf16(&g, stream))) return rc;                               // q = fc_q(norm1(o))
+    rc = ldt_attention_nk32(p.batch, p.heads, p.num_points, H / p.heads, p.ws_q, H, p.ws_kv,
+                            static_cast<const char*>(p.ws_kv) + 2 * static_cast<size_t>(H), 2 * H, p.ws_att, stream);
+    if (rc) return rc;
+    g.A = p.ws_att; g.W = L.w_o; g.bias = L.b_o; g.out = o; g.epilogue = LDT_EPI_GATE_RESID_F32; g.resid = o;
+    if ((rc = ldt_gemm_bf16(&g, stream))) return rc;                               // o = o + fc_o(att)           :225
+    if ((rc = ldt_layernorm_mod_bf16(MQ, H, o, nullptr, nullptr, 0, 1, L.norm2_w, L.norm2_b, 1e-6f, p.ws_a, stream))) return rc;
+    g.N = p.mlp_hidden; g.A = p.ws_a; g.W = L.w_fc1; g.bias = L.b_fc1; g.out = p.ws_hid; g.ldo = p.mlp_hidden;
+    g.epilogue = LDT_EPI_BIAS_GELU_BF16; g.resid = nullptr;
+    if ((rc = ldt_gemm_bf16(&g, stream))) return rc;
+    g.N = H; g.K = p.mlp_hidden; g.A = p.ws_hid; g.lda = p.mlp_hidden; g.W = L.w_fc2; g.ldw = p.mlp_hidden; g.bias = L.b_fc2;
+    g.out = o; g.ldo = H; g.epilogue = LDT_EPI_GATE_RESID_F32; g.resid = o;
+    if ((rc = ldt_gemm_bf16(&g, stream))) return rc;                               // o = o + mlp(norm2(o))       :226
+  }
+  if ((rc = ldt_cast_pad_bf16(MQ, H, o, H, p.ws_a, H, stream))) return rc;
+  g.M = MQ; g.N = 8; g.K = H; g.A = p.ws_a; g.lda = H; g.W = p.w_out; g.ldw = H; g.bias = p.b_out; g.out = points8; g.ldo = 8;
+  g.epilogue = LDT_EPI_BIAS_F32; g.resid = nullptr; g.gate = nullptr;
+  return ldt_gemm_bf16(&g, stream);                                                 // self.output(o)              :266
 }

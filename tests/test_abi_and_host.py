@@ -57,6 +57,7 @@ def test_argument_validation_without_gpu():
     assert L.ldt_score_forward(C.byref(plan), None, None, 0, None, None) == -3 and b"head dim 64" in L.ldt_last_error_string()
     assert L.ldt_score_forward(None, None, None, 0, None, None) == -1
     assert L.ldt_sample_loop(None, None) == -1
+    assert L.ldt_decoder_forward(None, None, None, None, None) == -1
 
 
 def test_state_dict_layout_matches_reference():

@@ -378,8 +378,9 @@ def test_fused_plan_is_captured_once_and_reused_across_generator_positions(dev):
 
 
 def test_whole_path_c_entry_points_equal_python_orchestration(dev):
-    """ldt_score_forward (one call per token pass) and ldt_sample_loop (one call per N-step loop, its own CUDA graph) issue
-    the same kernels in the same order as score.py::run_tokens / sampler.StepGraph: bit-identical results."""
+    """ldt_score_forward (one call per token pass), ldt_decoder_forward (one call per decode) and ldt_sample_loop (one call
+    per N-step loop, its own CUDA graph) issue the same kernels in the same order as score.py::run_tokens,
+    compressor.py::sample and sampler.StepGraph: bit-identical results."""
     from ldt_b200 import DiffusionVPSDE, sampler
     cfg = small_score_cfg()
     model, _ = build_score(cfg, 11, dev)
@@ -392,6 +393,16 @@ def test_whole_path_c_entry_points_equal_python_orchestration(dev):
         via_py = model(x, t)
         model.c_path = True
     assert torch.equal(via_c, via_py)
+    comp, _ = build_compressor(ns(airplane_config()).compressor, 13, dev)
+    eps = torch.randn((3, 32, 120), generator=g).to(dev)
+    for npts in (2048, 700):
+        torch.manual_seed(5)
+        p_c = comp.sample((3, npts), given_eps=eps)
+        comp.c_path = False
+        torch.manual_seed(5)
+        p_py = comp.sample((3, npts), given_eps=eps)
+        comp.c_path = True
+        assert torch.equal(p_c, p_py)
     sde = DiffusionVPSDE(ns(airplane_config()).sde, device=dev)
     tr = _Trainer(model, sde)
     outs = []
