@@ -143,6 +143,15 @@ __device__ __forceinline__ void epilogue_row32(const EpiParams& p, int row, int 
 // (the staging layout IS the 128-byte TMA swizzle; the buffer must be 1024-byte aligned) instead of 8 ld.shared + 8
 // st.global per lane: the per-SM store path through the LSU was costing the fc1 epilogue as much as its GELU arithmetic
 // (scripts/exp_epi.py).  The caller must run tma_store_wait_all()/..._read() on lane 0 before the buffer or the CTA goes away.
+#ifdef LDT_EPI_STAMPS   // variant builds only (scripts/exp_epi_stamps.py): clock64 stamps of the first epilogue warp of CTA 0
+#define LDT_STAMP(k)                                                                                          \
+  do {                                                                                                        \
+    if (p.dbg != nullptr && blockIdx.x == 0 && (threadIdx.x >> 5) == 0 && lane == 0) p.dbg[64 + (k)] = clock64(); \
+  } while (0)
+#else
+#define LDT_STAMP(k) do { } while (0)
+#endif
+
 template <int EPI, int NCOLS, int XM = 0, typename WaitFn>
 __device__ __forceinline__ void epilogue_staged(const EpiParams& p, uint8_t* stg, int lane, int row_base, int col_base,
                                                 uint32_t taddr, WaitFn wait_accumulator, const CUtensorMap* tm_out = nullptr) {
@@ -169,26 +178,49 @@ __device__ __forceinline__ void epilogue_staged(const EpiParams& p, uint8_t* stg
       }
     };
     if constexpr (EPI == LDT_EPI_GATE_RESID_F32) fetch_resid(0, r4[0]);
+    // Gate and bias of EVERY unit are fetched before the accumulator is waited for: they do not depend on the MMA, the
+    // inline-asm TMEM / shared-memory steps below are compiler barriers (a load written inside the loop is issued inside
+    // the loop), and each one is an L2 round trip -- in the loop they put one exposed ~700-cycle stall on every 32-column
+    // unit of a chain that is already the kernel's tail (scripts/exp_onetile.py: 10.4 k cycles per f32 tile epilogue).
+    float4 g4s[NU], b4s[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const int col = col_base + u * 32 + cc * 4;
+      g4s[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+      b4s[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (EPI == LDT_EPI_GATE_RESID_F32) {
+        if (col < p.N && p.gate != nullptr && gate_uniform && row_base < p.M)   // slabs past M (ragged last tile) have no gate row
+          g4s[u] = __ldg(reinterpret_cast<const float4*>(
+              p.gate + static_cast<long long>(row_base / p.rows_per_gate) * p.gate_stride + col));
+      }
+      if (col < p.N && p.bias != nullptr) b4s[u] = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    }
+    LDT_STAMP(0);
     wait_accumulator();
+    LDT_STAMP(1);
+    // The tile drains through four data paths of the SM: TMEM read (64 B/clk), shared-memory transpose, L2 reads (residual)
+    // and L2 writes.  All 8 epilogue warps run the same instruction stream from the same start, so written phase after
+    // phase every path is idle while another saturates (measured: ~2000 clk per 32-column unit, 8 k per tile,
+    // scripts/exp_epi_stamps.py).  The TMEM load of unit u+1 is therefore issued right after unit u's registers have been
+    // stored to the staging buffer -- into the SAME registers, which nothing touches until the wait -- so it streams in
+    // while unit u's 8 store rounds occupy the load/store path.
+    uint32_t v[32];
+    if (col_base < p.N) {
+      tmem_ld_32x32(taddr, v);
+      tmem_ld_wait();
+    }
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
       const int c0 = u * 32;
       const int col = col_base + c0 + cc * 4;
       const bool col_ok = col < p.N;   // N % 8 == 0 and col % 4 == 0: the whole float4 is inside
+      const bool next_live = (u + 1 < NU) && (col_base + c0 + 32 < p.N);   // warp-uniform
       if constexpr (EPI == LDT_EPI_GATE_RESID_F32) {
         if (u + 1 < NU) fetch_resid(u + 1, r4[(u + 1) & 1]);
       }
-      float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if constexpr (EPI == LDT_EPI_GATE_RESID_F32) {
-        if (col_ok && p.gate != nullptr && gate_uniform && row_base < p.M)   // slabs past M (ragged last tile) have no gate row
-          g4 = __ldg(reinterpret_cast<const float4*>(
-              p.gate + static_cast<long long>(row_base / p.rows_per_gate) * p.gate_stride + col));
-      }
-      if (col_ok && p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      const float4 g4 = g4s[u], b4 = b4s[u];
       if (col_base + c0 < p.N) {   // warp-uniform: this unit has at least one live column
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), v);
-        tmem_ld_wait();
+        LDT_STAMP(2 + 4 * u);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const uint32_t a = st_row + static_cast<uint32_t>((c ^ (lane & 7)) << 4);
@@ -197,6 +229,11 @@ __device__ __forceinline__ void epilogue_staged(const EpiParams& p, uint8_t* stg
                        : "memory");
         }
         __syncwarp();
+        LDT_STAMP(3 + 4 * u);
+#ifndef LDT_EPI_NO_TMEM_PIPELINE   // (A/B builds: the load issued after the store rounds instead, i.e. phase after phase)
+        if (next_live) tmem_ld_32x32(taddr + static_cast<uint32_t>(c0 + 32), v);   // in flight during the store rounds
+#endif
+        LDT_STAMP(4 + 4 * u);
         if (col_ok) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -242,6 +279,11 @@ __device__ __forceinline__ void epilogue_staged(const EpiParams& p, uint8_t* stg
           }
         }
         __syncwarp();
+#ifdef LDT_EPI_NO_TMEM_PIPELINE
+        if (next_live) tmem_ld_32x32(taddr + static_cast<uint32_t>(c0 + 32), v);
+#endif
+        if (next_live) tmem_ld_wait();
+        LDT_STAMP(5 + 4 * u);
       }
     }
   } else {

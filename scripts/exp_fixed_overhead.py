@@ -44,3 +44,16 @@ for M in (512, 2048, 8192):
             kw = dict(resid=out, gate=gate, gate_stride=N, rows_per_gate=32) if epi == 3 else {}
             res.append(graph_time(lambda: ops.gemm(A, W, b, out, epi, **kw)))
         print(f"M={M:5d} {name:18s}: K=64 {res[0]:6.2f} us   K={K} {res[1]:6.2f} us   -> mainloop part {res[1] - res[0]:6.2f} us", flush=True)
+
+# floors: an empty-ish kernel, and a one-tile GEMM (one CTA pair, one k-block)
+step = torch.zeros(1, dtype=torch.int32, device=dev)
+print(f"graph launch floor (1-thread kernel): {graph_time(lambda: ops.advance_step(step)):.2f} us", flush=True)
+x32 = torch.randn((2048, 1024), device=dev)
+a16 = torch.empty((2048, 1024), dtype=torch.bfloat16, device=dev)
+print(f"LayerNorm M=2048: {graph_time(lambda: ops.layernorm_mod(x32, a16)):.2f} us", flush=True)
+for M, N in ((256, 256), (256, 1024), (2048, 1024)):
+    A = torch.randn((M, 64), device=dev).bfloat16()
+    W = torch.randn((N, 64), device=dev).bfloat16()
+    b = torch.randn((N,), device=dev)
+    o16 = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+    print(f"one-k-block GEMM M={M} N={N} bias->bf16: {graph_time(lambda: ops.gemm(A, W, b, o16, 1)):.2f} us", flush=True)
