@@ -25,6 +25,7 @@ from .sde import _PRED_CODES, torch_randn_launch_geometry
 
 
 _warned: set = set()
+_verified = weakref.WeakSet()   # score_fn function objects whose probe passed (one probe per function, not per sample() call)
 
 
 def _warn_once(key: str, msg: str) -> None:
@@ -52,6 +53,9 @@ def find_score_module(score_fn, sde, probe=None):
         _warn_once("sde", "ldt_b200: score_fn is bound to an ldt_b200.Score but to another SDE object; sampling runs "
                           "the generic per-step path, not the fused CUDA-graph loop")
         return None
+    func = getattr(score_fn, "__func__", None)
+    if probe is not None and func is not None and func in _verified:
+        probe = None    # this very function object already reproduced the hard-wired pair on a real call
     if probe is not None:
         t, x, label, condition = probe
         try:
@@ -63,6 +67,11 @@ def find_score_module(score_fn, sde, probe=None):
                   and torch.equal(got[0], score))
         except Exception:   # a closure with another signature: not ours to fuse
             ok = False
+        if ok and func is not None:
+            try:
+                _verified.add(func)
+            except TypeError:
+                pass
         if not ok:
             _warn_once("probe", "ldt_b200: score_fn does not compute (-model(x, t) / sqrt(SDE.var(t)), model(x, t)); sampling "
                                 "runs the generic per-step path, not the fused CUDA-graph loop")
