@@ -22,7 +22,11 @@ template <int BN>
 struct Tc2Cfg {
   static constexpr int A_BYTES = 128 * TC_BK * 2;
   static constexpr int B_BYTES = (BN / 2) * TC_BK * 2;
+#ifdef LDT_T2_STAGES   // A/B builds only
+  static constexpr int STAGES = LDT_T2_STAGES;
+#else
   static constexpr int STAGES = (BN == 256) ? 6 : 8;
+#endif
   static constexpr int ACC_STRIDE = (BN > 128) ? 256 : 128;   // column offset between the two accumulators
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int SMEM_BYTES =
