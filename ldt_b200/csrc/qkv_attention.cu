@@ -251,6 +251,9 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       tc_fence_before();
       fence_proxy_async_smem();
       qa_bar_sync(1 + set, 128);     // all four samples' Q, K, V are in place and out of the accumulator columns
+#ifdef LDT_QA_EARLY_RELEASE   // timing experiment only (results are WRONG): hand the accumulator back right after the drain
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[set]), 0));
+#endif
 
       // ---- S[128 x 128] = Q K^T into accumulator columns [0,128) ----
       if (issuer) {
@@ -311,7 +314,9 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
+#ifndef LDT_QA_EARLY_RELEASE
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[set]), 0));   // the accumulator slot is free again
+#endif
 
       // ---- O / sum -> bf16 -> this row of the (now idle) K tile -> one contiguous 4 KB block per (sample, head) ----
 #pragma unroll
