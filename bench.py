@@ -9,9 +9,14 @@ only collective is the final all-gather of generated points).
   value      clouds/s, whole job, latents already in HBM when the timed region starts
   e2e        the same through the reference-facing API (DiffusionVPSDE.sample_discrete + Compressor.sample, i.e.
              what Trainer.sample calls) with host buffers: CPU-generator x0 -> H2D inside, points D2H inside
-  roofline   the dense-contraction kernel (tcgen05 GEMM): algorithmic FLOPs / CUDA-event kernel time, vs the
-             measured cuBLAS bf16 peak in MEASURED_PEAKS.json
-  cd         secondary metric of BASELINE.json: Chamfer cloud-pairs/s (2048-point clouds)
+  roofline   the dense-contraction kernels (tcgen05): algorithmic FLOPs / in-graph marginal time of each kernel class
+             (the token pass captured in a CUDA graph, re-captured with one class removed: ldt_b200/profiling.py), vs the
+             measured sustained cuBLAS bf16 peak in MEASURED_PEAKS.json; per-kernel fractions in roofline.per_kernel
+  cd         BASELINE.json configs[3]: the 2048 x 2048 Chamfer matrix (2048 points per cloud), rows sharded over ALL
+             ranks, NCCL gather; plus the symmetric (upper-triangle) form and a roofline against the FP32-FMA rate
+             measured in the same run
+  completion BASELINE.json configs[4] shape (64 clouds per GPU on every rank, ConditionNet prologue inside)
+  gpu_eager_baseline   the reference's op sequence (oracle port) run eagerly on the same GPU, TF32 on / off
   cpu_baseline / --impl reference: the oracle port of the reference's CPU path on the host cores (bounded sample)
 """
 import argparse
