@@ -167,11 +167,26 @@ __device__ __forceinline__ void epilogue_staged(const EpiParams& p, uint8_t* stg
     constexpr int NU = NCOLS / 32;
     // one gate row for the whole 32-row slab (rows_per_gate a multiple of 32, e.g. the 32 latent tokens of a sample)?
     const bool gate_uniform = (p.rows_per_gate & 31) == 0 && (row_base & 31) == 0;
+    // FAST (warp-uniform): the whole 32-row x NCOLS slab is inside the matrix and the gate is one row per slab -- every
+    // tile of the score net except a ragged last one.  The per-round row / column predicates, the 64-bit address
+    // products and the per-row gate branch then disappear from the 8 load-add-store rounds of a unit: the epilogue of a
+    // tile is ~1000 warp-instructions of one dependent chain per warp (two such warps per scheduler), i.e. bound by
+    // instruction latency, not by TMEM / shared-memory / L2 throughput (scripts/exp_onetile.py: 8 k cycles per tile with the
+    // global loads and stores compiled out), so instructions removed from the rounds are time removed from the tail.
+    const bool fast = (row_base + 32 <= p.M) && (col_base + NCOLS <= p.N) && (p.gate == nullptr || gate_uniform);
+    const size_t off0 = static_cast<size_t>(row_base + rr0) * p.ldo + col_base + cc * 4;   // (first row, first chunk) of this lane
+    const size_t pitch = static_cast<size_t>(4) * p.ldo;                                    // one round further = 4 rows
     // Residual rows are software-pipelined one unit ahead (and unit 0 is fetched BEFORE the accumulator is waited
     // for): they do not depend on the MMA, and with <= 1 KB of L1 left beside 225 KB of shared memory every one of
     // them is an L2 round trip.  out may alias resid element for element; a unit's loads precede its stores.
     float4 r4[2][8];
     auto fetch_resid = [&](int u, float4(&r)[8]) {
+      if (fast) {
+        const float* src = p.resid + off0 + u * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = __ldcg(reinterpret_cast<const float4*>(src + i * pitch));
+        return;
+      }
       const int col = col_base + u * 32 + cc * 4;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -184,8 +199,7 @@ __device__ __forceinline__ void epilogue_staged(const EpiParams& p, uint8_t* stg
     if constexpr (EPI == LDT_EPI_GATE_RESID_F32) fetch_resid(0, r4[0]);
     // Gate and bias of EVERY unit are fetched before the accumulator is waited for: they do not depend on the MMA, the
     // inline-asm TMEM / shared-memory steps below are compiler barriers (a load written inside the loop is issued inside
-    // the loop), and each one is an L2 round trip -- in the loop they put one exposed ~700-cycle stall on every 32-column
-    // unit of a chain that is already the kernel's tail (scripts/exp_onetile.py: 10.4 k cycles per f32 tile epilogue).
+    // the loop), and each one is an L2 round trip.
     float4 g4s[NU], b4s[NU];
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
@@ -199,15 +213,36 @@ __device__ __forceinline__ void epilogue_staged(const EpiParams& p, uint8_t* stg
       }
       if (col < p.N && p.bias != nullptr) b4s[u] = __ldg(reinterpret_cast<const float4*>(p.bias + col));
     }
+    // one load-add-store round: staged row rr0 + 4*i, 16-byte chunk cc -> bias, gate, residual -> global
+    auto finish = [&](float4 a4, const float4& g, const float4& b4, const float4& r) -> float4 {
+#ifdef LDT_EPI_SCALAR_F32   // A/B builds only
+      a4.x += b4.x; a4.y += b4.y; a4.z += b4.z; a4.w += b4.w;
+      if constexpr (EPI == LDT_EPI_GATE_RESID_F32) {
+        a4.x = r.x + g.x * a4.x; a4.y = r.y + g.y * a4.y;
+        a4.z = r.z + g.z * a4.z; a4.w = r.w + g.w * a4.w;
+      }
+#else
+      // packed fp32 (FADD2 / FFMA2), two columns per instruction; each half rounds like the scalar form
+      uint64_t lo = add_f32x2(pack_f32x2(a4.x, a4.y), pack_f32x2(b4.x, b4.y));
+      uint64_t hi = add_f32x2(pack_f32x2(a4.z, a4.w), pack_f32x2(b4.z, b4.w));
+      if constexpr (EPI == LDT_EPI_GATE_RESID_F32) {
+        lo = fma_f32x2(pack_f32x2(g.x, g.y), lo, pack_f32x2(r.x, r.y));
+        hi = fma_f32x2(pack_f32x2(g.z, g.w), hi, pack_f32x2(r.z, r.w));
+      }
+      unpack_f32x2(lo, a4.x, a4.y);
+      unpack_f32x2(hi, a4.z, a4.w);
+#endif
+      if constexpr (EPI == LDT_EPI_BIAS_GELU_F32) {   // TF32 parity mode: exact-erf GELU, rounded to TF32
+        a4.x = round_tf32(gelu_erf_f(a4.x)); a4.y = round_tf32(gelu_erf_f(a4.y));
+        a4.z = round_tf32(gelu_erf_f(a4.z)); a4.w = round_tf32(gelu_erf_f(a4.w));
+      }
+      return a4;
+    };
     LDT_STAMP(0);
     wait_accumulator();
     LDT_STAMP(1);
-    // The tile drains through four data paths of the SM: TMEM read (64 B/clk), shared-memory transpose, L2 reads (residual)
-    // and L2 writes.  All 8 epilogue warps run the same instruction stream from the same start, so written phase after
-    // phase every path is idle while another saturates (measured: ~2000 clk per 32-column unit, 8 k per tile,
-    // scripts/exp_epi_stamps.py).  The TMEM load of unit u+1 is therefore issued right after unit u's registers have been
-    // stored to the staging buffer -- into the SAME registers, which nothing touches until the wait -- so it streams in
-    // while unit u's 8 store rounds occupy the load/store path.
+    // The TMEM load of unit u+1 is issued right after unit u's registers have been stored to the staging buffer -- into the
+    // SAME registers, which nothing touches until the wait -- so it streams in while unit u's 8 store rounds run.
     uint32_t v[32];
     if (col_base < p.N) {
       tmem_ld_32x32(taddr, v);
@@ -238,7 +273,18 @@ __device__ __forceinline__ void epilogue_staged(const EpiParams& p, uint8_t* stg
         if (next_live) tmem_ld_32x32(taddr + static_cast<uint32_t>(c0 + 32), v);   // in flight during the store rounds
 #endif
         LDT_STAMP(4 + 4 * u);
-        if (col_ok) {
+        if (fast) {
+          float* dst = static_cast<float*>(p.out) + off0 + c0;
+          const uint32_t lds0 = stg_u32 + static_cast<uint32_t>(rr0 * 128);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = rr0 + 4 * i;   // (rr & 7) == (rr0 + 4 * (i & 1)) & 7: two swizzle phases per lane
+            float4 a4;
+            const uint32_t a = lds0 + static_cast<uint32_t>(i * 512 + ((cc ^ (rr & 7)) << 4));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w) : "r"(a));
+            *reinterpret_cast<float4*>(dst + i * pitch) = finish(a4, g4, b4, r4[u & 1][i]);
+          }
+        } else if (col_ok) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = rr0 + 4 * i;
@@ -247,38 +293,14 @@ __device__ __forceinline__ void epilogue_staged(const EpiParams& p, uint8_t* stg
             const uint32_t a = stg_u32 + static_cast<uint32_t>(rr * 128 + ((cc ^ (rr & 7)) << 4));
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w) : "r"(a));
             if (row < p.M) {
-#ifdef LDT_EPI_SCALAR_F32   // A/B builds only
-              a4.x += b4.x; a4.y += b4.y; a4.z += b4.z; a4.w += b4.w;
+              float4 g = g4;
               if constexpr (EPI == LDT_EPI_GATE_RESID_F32) {
-                float4 g = g4;
                 if (p.gate != nullptr && !gate_uniform)
                   g = __ldg(reinterpret_cast<const float4*>(
                       p.gate + static_cast<long long>(row / p.rows_per_gate) * p.gate_stride + col));
-                const float4 r = r4[u & 1][i];
-                a4.x = r.x + g.x * a4.x; a4.y = r.y + g.y * a4.y;
-                a4.z = r.z + g.z * a4.z; a4.w = r.w + g.w * a4.w;
               }
-#else
-              // packed fp32 (FADD2 / FFMA2), two columns per instruction; each half rounds like the scalar form
-              uint64_t lo = add_f32x2(pack_f32x2(a4.x, a4.y), pack_f32x2(b4.x, b4.y));
-              uint64_t hi = add_f32x2(pack_f32x2(a4.z, a4.w), pack_f32x2(b4.z, b4.w));
-              if constexpr (EPI == LDT_EPI_GATE_RESID_F32) {
-                float4 g = g4;
-                if (p.gate != nullptr && !gate_uniform)
-                  g = __ldg(reinterpret_cast<const float4*>(
-                      p.gate + static_cast<long long>(row / p.rows_per_gate) * p.gate_stride + col));
-                const float4 r = r4[u & 1][i];
-                lo = fma_f32x2(pack_f32x2(g.x, g.y), lo, pack_f32x2(r.x, r.y));
-                hi = fma_f32x2(pack_f32x2(g.z, g.w), hi, pack_f32x2(r.z, r.w));
-              }
-              unpack_f32x2(lo, a4.x, a4.y);
-              unpack_f32x2(hi, a4.z, a4.w);
-#endif
-              if constexpr (EPI == LDT_EPI_BIAS_GELU_F32) {   // TF32 parity mode: exact-erf GELU, rounded to TF32
-                a4.x = round_tf32(gelu_erf_f(a4.x)); a4.y = round_tf32(gelu_erf_f(a4.y));
-                a4.z = round_tf32(gelu_erf_f(a4.z)); a4.w = round_tf32(gelu_erf_f(a4.w));
-              }
-              *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col) = a4;
+              *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col) =
+                  finish(a4, g, b4, r4[u & 1][i]);
             }
           }
         }
