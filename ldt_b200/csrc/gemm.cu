@@ -382,7 +382,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
-    if (tm_out != nullptr && lane == 0) tma_store_wait_all();   // the staging buffer outlives its last bulk store
+    if (tm_out != nullptr && lane == 0) tma_store_wait_read();   // the staging buffer outlives the last bulk store's READ; the writes complete with the grid
     if constexpr (DBG) {
       if (p.dbg && warp == TC_EPI_WARP0 && lane == 0) {
         p.dbg[blockIdx.x * 8 + 3] = clock64() - t_begin;

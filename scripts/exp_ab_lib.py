@@ -14,7 +14,7 @@ from ldt_b200 import _lib, ops  # noqa: E402
 from scripts.exp_gemm_limits import graph_of, timed_with_clocks  # noqa: E402
 
 dev = torch.device("cuda:0")
-M = 8192
+M = int(os.environ.get("LDT_AB_M", "8192"))
 SH = {"qkv": (3072, 1024, 1), "fc_o": (1024, 1024, 3), "fc1": (4096, 1024, 2), "fc2": (1024, 4096, 3)}
 
 
