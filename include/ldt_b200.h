@@ -96,6 +96,11 @@ enum ldt_epilogue {
                                  be NULL (= 1): x + gate*f(x) of layers.py:218-219,225-226           */
   LDT_EPI_BIAS_GELU_F32 = 4,  /* out f32  = tf32_round(gelu_erf(acc + bias)): the MLP hidden of the TF32 parity mode
                                  (operand_type 1), rounded because it is the A operand of the next contraction */
+  LDT_EPI_BIAS_RELU_F32 = 5,  /* out f32  = max(acc + bias, 0): Conv1d(k=1) + BatchNorm1d (folded into W and
+                                 bias by the host) + ReLU of the encoder prologue (ConvBNReLU1D, Compressor/layers.py:115-127;
+                                 MiniPointnet, Network.py:94-95)                                     */
+  LDT_EPI_RESID_RELU_F32 = 6, /* out f32  = max(resid + acc + bias, 0): ConvBNReLURes1D's act(net2(net1(x)) + x),
+                                 Compressor/layers.py:159-160; no gate                               */
 };
 
 typedef struct ldt_gemm_args {
@@ -209,6 +214,14 @@ int ldt_time_embedding(int R, int half, int D, const float* t, const float* freq
  *   ldt_attention_nk32_f32  ldt_attention_nk32 on f32 q/k/v (dh in {32, 64}), fp32 softmax, TF32-rounded f32 output
  * ------------------------------------------------------------------------------------------------ */
 int ldt_round_pad_tf32(long long rows, int cols, const float* in, int ld_in, float* out, int ld_out, int silu, void* stream);
+
+/* Error-compensated TF32 operands ("3xTF32") for fp32-grade contractions on the tensor cores: in f32 [rows, ld_in] ->
+ * out f32 [rows, 3*ld_part], v = hi + lo with hi = tf32(v), lo = tf32(v - hi); an activation row becomes [hi | hi | lo], a
+ * weight row (weight_side = 1) [hi | lo | hi], each part zero-padded to ld_part columns, so that ONE ldt_gemm_bf16 call with
+ * operand_type 1 and K = 3*ld_part computes a_hi.w_hi + a_hi.w_lo + a_lo.w_hi.  Used for the fp32 Conv1d / Linear layers of
+ * the encoder and condition prologues (model/Compressor/Network.py:192, layers.py:115-160, scorenet/score.py:36-41), which
+ * the reference evaluates in fp32. */
+int ldt_split_tf32(long long rows, int cols, const float* in, int ld_in, float* out, int ld_part, int weight_side, void* stream);
 int ldt_layernorm_mod_f32(int rows, int C, const float* x, const float* shift, const float* scale, long long mod_stride,
                           int rows_per_mod, const float* weight, const float* bias, float eps, float* y, void* stream);
 int ldt_attention_nk32_f32(int B, int H, int Nq, int dh, const float* q, int ldq, const float* k, const float* v, int ldkv,
@@ -415,6 +428,21 @@ int ldt_furthest_point_sample(int b, int n, int m, const float* xyz, float min_s
  * increasing squared distance (ties -> lowest index).  Replaces knn_point = square_distance + torch.topk
  * (model/Compressor/layers.py:63-98), which builds a dense [b,s,n] matrix and returns the set in unspecified order. */
 int ldt_knn_indices(int b, int n, int s, int k, const float* xyz, const float* centers, int* idx, void* stream);
+
+/* LocalGrouper's normalised group features (model/Compressor/layers.py:300-317), written as the A operand of
+ * PreExtraction's first 1x1 convolution: out [b*s*k, ld_out] f32 (columns >= 2d+3 zero), row (b,s,j) =
+ *     cat( alpha * ((g - mean) / (std_b + 1e-5)) + beta ,  fea[b, center_idx[b,s], :] )
+ * with g = cat(fea[b, group_idx[b,s,j], :], xyz[b, group_idx[b,s,j], :]) (use_xyz=True), mean = the anchor's own
+ * cat(fea, xyz) (normalize 2, "anchor"), the mean of g over the k neighbours (1, "center"), or no normalisation at all (0),
+ * and std_b the unbiased standard deviation of all (g - mean) of sample b.  xyz [b,n,3], fea [b,n,d] f32, indices i32;
+ * alpha / beta [d+3]; partial = 2*b*s doubles of scratch.  Deterministic (fixed-order sums, no atomics). */
+int ldt_group_features(int b, int n, int s, int k, int d, const float* xyz, const float* fea, const int* center_idx,
+                       const int* group_idx, int normalize, const float* alpha, const float* beta, double* partial, float* out,
+                       int ld_out, void* stream);
+
+/* out[g, c] = max over j < k of x[g*k + j, c]  (f32; x [groups*k, ldx], out [groups, ldo]): the max over a group's neighbours
+ * that ends PreExtraction (model/Compressor/layers.py:189-190) and MiniPointnet (model/Compressor/Network.py:97). */
+int ldt_group_max(int groups, int k, int c, const float* x, int ldx, float* out, int ldo, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Device properties needed by the host mirror

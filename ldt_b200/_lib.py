@@ -19,6 +19,8 @@ EPI_BIAS_BF16 = 1
 EPI_BIAS_GELU_BF16 = 2
 EPI_GATE_RESID_F32 = 3
 EPI_BIAS_GELU_F32 = 4
+EPI_BIAS_RELU_F32 = 5
+EPI_RESID_RELU_F32 = 6
 
 PRED_ANCESTRAL = 0
 PRED_REVERSE_DIFFUSION = 1
@@ -149,6 +151,9 @@ PROTOTYPES = {
     "ldt_cond_silu": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldt_furthest_point_sample": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "ldt_knn_indices": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldt_group_features": (C.c_int, [C.c_int] * 5 + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p]),
+    "ldt_split_tf32": (C.c_int, [C.c_longlong, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "ldt_group_max": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
 }
 
 _lib = None

@@ -13,15 +13,16 @@ model/layers.py:224-226); finally Conv1d(hidden->3).
 ``forward(x)`` (bottom_up + top_down, Network.py:188-249: the inference path of the set-VAE encoder)
 runs on the same kernels: FPS + k-NN grouping (``ldt_furthest_point_sample`` / ``ldt_knn_indices``), the AdaLN encoder
 blocks on the 32 group tokens, the posterior blocks whose 32 tokens attend to the 2048 decoded points
-(``ldt_attention_longkv``), and the decoder blocks above.  The small point-wise layers around the grouping (input
-Conv1d(3->hidden), the grouper's Conv+BatchNorm stack, MiniPointnet, ActNorm) are evaluated with torch functional ops
-straight from the parameters.  Inference only: the KL terms are returned, nothing is differentiable.
+(``ldt_attention_longkv``), and the decoder blocks above.  The point-wise layers around the grouping (input
+Conv1d(3->hidden), the grouper's Conv + BatchNorm + ReLU stack, MiniPointnet) are error-compensated kind::tf32 contractions
+("3xTF32", fp32-grade) of the same GEMM core with the eval-mode BatchNorm folded into the weights and the ReLU / residual in the epilogue; gather + normalise +
+concatenate and the max over neighbours are ``ldt_group_features`` / ``ldt_group_max`` (``grouping.py``).  Only ActNorm's
+per-channel affine is a torch expression.  Inference only: the KL terms are returned, nothing is differentiable.
 """
 from __future__ import annotations
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import ops
 from ._lib import EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_GATE_RESID_F32
@@ -235,6 +236,7 @@ class Compressor(nn.Module):
         """Drop the packed bf16 weights; needed only after in-place writes through ``.data`` (see Score.invalidate_packed)."""
         self._packed = None
         self._packed_key = None
+        self._packed_pro = None
         self._generation = getattr(self, "_generation", 0) + 1
 
     def packed(self):
@@ -386,34 +388,22 @@ class Compressor(nn.Module):
     # ------------------------------------------------------------------------------------------
     # encoder inference path
     # ------------------------------------------------------------------------------------------
-    def _bn(self, m, x):
-        return F.batch_norm(x, m.running_mean, m.running_var, m.weight, m.bias, training=False, eps=1e-5)
-
-    def _group(self, g, normalize, xyz, feature, groups, k):
-        """LocalGrouper.forward (Compressor/layers.py:288-319) from the parameters of sub-tree ``g``; FPS and k-NN on the
-        sm_100a kernels.  xyz [B,3,N], feature [B,D,N] -> (centres [B,3,S], group features [B,D,S])."""
-        from .condition import cluster, gather_points
-        pts, fea = xyz.transpose(1, 2), feature.transpose(1, 2)
-        B = pts.shape[0]
-        new_xyz, fps_idx, idx = cluster(pts, groups, k)
-        anchor = gather_points(fea, fps_idx)
-        grouped = torch.cat([gather_points(fea, idx), gather_points(pts, idx)], dim=-1)
-        normalize = normalize.lower() if isinstance(normalize, str) else None
-        if normalize in ("center", "anchor"):
-            mean = grouped.mean(dim=2, keepdim=True) if normalize == "center" else torch.cat([anchor, new_xyz], dim=-1).unsqueeze(-2)
-            centred = grouped - mean
-            std = torch.std(centred.reshape(B, -1), dim=-1, keepdim=True)[:, :, None, None]
-            grouped = g.affine_alpha * (centred / (std + 1e-5)) + g.affine_beta
-        x = torch.cat([grouped, anchor.unsqueeze(2).expand(-1, -1, k, -1)], dim=-1)
-        b, s_, kk, d = x.shape
-        x = x.permute(0, 1, 3, 2).reshape(b * s_, d, kk)
-        ex = g.extraction
-        t = ex.transfer.net
-        x = F.relu(self._bn(t._modules["1"], F.conv1d(x, t._modules["0"].weight, t._modules["0"].bias)))
-        op = ex.operation._modules["0"]
-        y = F.relu(self._bn(op.net1._modules["1"], F.conv1d(x, op.net1._modules["0"].weight, op.net1._modules["0"].bias)))
-        x = F.relu(F.conv1d(y, op.net2._modules["0"].weight, op.net2._modules["0"].bias) + x)
-        return new_xyz.transpose(1, 2), x.amax(dim=-1).reshape(b, s_, -1).permute(0, 2, 1)
+    def _packed_prologue(self):
+        """Folded TF32 weights of the point-wise layers in front of the encoder blocks (input Conv1d, the groupers'
+        Conv + BatchNorm stacks, MiniPointnet); cached like :meth:`packed`, keyed on parameters AND BatchNorm buffers."""
+        from . import grouping
+        pre = ("input.", "group.", "pre_grouper.", "pos_embedding.")
+        key = (getattr(self, "_generation", 0),) + tuple(
+            (t.data_ptr(), t._version) for n, t in list(self.named_parameters()) + list(self.named_buffers()) if n.startswith(pre))
+        if getattr(self, "_packed_pro", None) is not None and key == self._packed_pro_key:
+            return self._packed_pro
+        with torch.no_grad():
+            P = {"input": grouping.pack_tf32(self.input), "group": grouping.pack_grouper(self.group),
+                 "pos": grouping.pack_mini_pointnet(self.pos_embedding)}
+            if self.cfg.pre_group:
+                P["pre_grouper"] = grouping.pack_grouper(self.pre_grouper)
+        self._packed_pro, self._packed_pro_key = P, key
+        return P
 
     def _attn_block(self, W, B, x, kv_src, kv_tokens, n1, n2, gate1, gate2, bufs, mod_stride=0):
         """One ResidualBlock on the 32 group tokens with K/V taken from ``kv_src`` (bf16 [B*kv_tokens, H], NOT normalised:
@@ -434,6 +424,30 @@ class Compressor(nn.Module):
         ops.gemm(a, W["w_fc1"], W["b_fc1"], hid, EPI_BIAS_GELU_BF16)
         ops.gemm(hid, W["w_fc2"], W["b_fc2"], x, EPI_GATE_RESID_F32, resid=x, gate=gate2, gate_stride=mod_stride, rows_per_gate=T)
 
+    def encoder_prologue(self, pts):
+        """Network.py:189-199: points [B,N,3] -> (group tokens [B, 32, H] f32 after ActNorm, position embedding [B, p_dim])."""
+        cfg = self.cfg
+        dev = self.output.weight.device
+        H, T = self.hidden_dim, self.z_scales
+        pts = pts.to(dev).float()
+        if cfg.norm_input:
+            pts = (pts - pts.mean(dim=1, keepdim=True)) / pts.std(dim=1, keepdim=True)
+        B, N = pts.shape[0], pts.shape[1]
+        from . import grouping
+        Q = self._packed_prologue()
+        pts = pts.contiguous()
+        # input Conv1d(3 -> hidden) on every point (Network.py:192), rows [B*N, hidden]
+        x = grouping.conv_rows(pts.reshape(B * N, 3), Q["input"]).reshape(B, N, H)
+        if cfg.pre_group:
+            pts, x = grouping.local_group(self.pre_grouper, Q["pre_grouper"], cfg.cluster_norm, pts, x, 256, 32)
+            x = x.reshape(B, 256, H)
+        center, x = grouping.local_group(self.group, Q["group"], cfg.cluster_norm, pts, x, T, pts.shape[1] // T * 2)
+        pos = grouping.mini_pointnet(Q["pos"], center)                     # MiniPointnet, Network.py:86-101 -> [B, p_dim]
+        x = x.reshape(B, T, H)                                             # [B, 32, H] token-major
+        if self.ActNorm is not None:
+            x = (x - self.conv_in.shift) * torch.exp(-self.conv_in.log_scale)   # ActNorm.forward, model/layers.py:103-107
+        return x, pos
+
     def bottom_up(self, pts, label=None):
         """Network.py:188-209: points [B,N,3] -> per-layer encoder outputs (token-major f32 [B*32, H]) and max feature."""
         cfg = self.cfg
@@ -446,22 +460,8 @@ class Compressor(nn.Module):
             raise NotImplementedError("ldt_b200.Compressor is an inference path: encoder_dropout_p must be 0")
         P = self.packed()
         H, T, Pd = self.hidden_dim, self.z_scales, self.p_dim
-        pts = pts.to(dev).float()
-        if cfg.norm_input:
-            pts = (pts - pts.mean(dim=1, keepdim=True)) / pts.std(dim=1, keepdim=True)
-        B = pts.shape[0]
-        pts = pts.transpose(1, 2)
-        x = F.conv1d(pts, self.input.weight, self.input.bias)
-        if cfg.pre_group:
-            pts, x = self._group(self.pre_grouper, cfg.cluster_norm, pts, x, 256, 32)
-        center, x = self._group(self.group, cfg.cluster_norm, pts, x, T, pts.shape[2] // T * 2)
-        pe = self.pos_embedding                                           # MiniPointnet, Network.py:86-101
-        y = F.relu(self._bn(pe.bn1, F.conv1d(center, pe.conv1.weight, pe.conv1.bias)))
-        y = F.relu(self._bn(pe.bn2, F.conv1d(y, pe.conv2.weight, pe.conv2.bias)))
-        pos = F.linear(y.amax(dim=2), pe.fc.weight, pe.fc.bias).contiguous()    # [B, p_dim]
-        x = x.transpose(1, 2)                                              # [B, 32, H]
-        if self.ActNorm is not None:
-            x = (x - self.conv_in.shift) * torch.exp(-self.conv_in.log_scale)   # ActNorm.forward, model/layers.py:103-107
+        x, pos = self.encoder_prologue(pts)
+        B = x.shape[0]
         x = x.reshape(B * T, H).contiguous()                               # token-major residual stream
         # all adaLN rows of the encoder from SiLU(pos) in one GEMM
         sc = torch.empty((B, Pd), dtype=torch.bfloat16, device=dev)

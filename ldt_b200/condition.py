@@ -4,9 +4,11 @@
 Runs ONCE per ``sample()`` call, before the reverse-SDE loop (completion_trainer/Latent_SDE_Trainer.py:150-151), so
 it is a prologue, not the hot loop.  What is B200-native here is the point-set part the reference cannot run without
 its un-vendored ``pointnet2_ops`` dependency: furthest point sampling and k-NN grouping are sm_100a kernels behind the
-C ABI (``ldt_furthest_point_sample``, ``ldt_knn_indices``); the small dense layers around them (ResNet18 stem on the
-image, 1x1 convolutions with BatchNorm on 32 groups x 8 neighbours) are plain torch modules with the reference's
-parameter names, so reference checkpoints load with ``strict=True``:
+C ABI (``ldt_furthest_point_sample``, ``ldt_knn_indices``), and the 1x1 convolutions with BatchNorm around them run as
+error-compensated kind::tf32 contractions of the library's GEMM core (``grouping.py``: fp32-grade "3xTF32", BatchNorm folded, ReLU / residual in the epilogue,
+``ldt_group_features`` / ``ldt_group_max``).  The ResNet18 stem on the image stays a torch / cuDNN module (SURVEY.md A10
+allows it: once per call, outside the loop).  The modules keep the reference's parameter names, so reference checkpoints
+load with ``strict=True``:
 
   c_net.pc_conv_in, c_net.group.{affine_alpha, affine_beta, extraction.transfer.net.{0,1},
   extraction.operation.0.{net1.{0,1}, net2.0}}, c_net.pc_conv_out, c_net.resnet.{0,1,4,5}.*, c_net.ln, c_net.conv_out
@@ -46,40 +48,30 @@ def cluster(xyz: torch.Tensor, groups: int, k: int, center=None):
 
 
 class _ConvBNAct(nn.Module):
-    """Conv1d(k=1) + BatchNorm1d + ReLU under the key ``net`` (ConvBNReLU1D, Compressor/layers.py:115-127)."""
+    """Parameters of Conv1d(k=1) + BatchNorm1d + ReLU under the key ``net`` (ConvBNReLU1D, Compressor/layers.py:115-127).
+    A parameter container: the arithmetic is ``grouping.local_group`` on the library's kernels."""
 
     def __init__(self, cin, cout):
         super().__init__()
         self.net = nn.Sequential(nn.Conv1d(cin, cout, 1), nn.BatchNorm1d(cout), nn.ReLU(inplace=True))
 
-    def forward(self, x):
-        return self.net(x)
-
 
 class _ConvBNActRes(nn.Module):
-    """Residual 1x1 block, keys ``net1`` / ``net2`` (ConvBNReLURes1D with groups=1, Compressor/layers.py:130-160)."""
+    """Parameters of the residual 1x1 block, keys ``net1`` / ``net2`` (ConvBNReLURes1D with groups=1, layers.py:130-160)."""
 
     def __init__(self, ch):
         super().__init__()
         self.net1 = nn.Sequential(nn.Conv1d(ch, ch, 1), nn.BatchNorm1d(ch), nn.ReLU(inplace=True))
         self.net2 = nn.Sequential(nn.Conv1d(ch, ch, 1))
 
-    def forward(self, x):
-        return F.relu(self.net2(self.net1(x)) + x)
-
 
 class _PreExtraction(nn.Module):
-    """[B,S,k,d] -> [B,D,S]: per-neighbour 1x1 layers then max over the k neighbours (Compressor/layers.py:163-192)."""
+    """Parameters of PreExtraction (Compressor/layers.py:163-192): ``transfer`` + one residual block."""
 
     def __init__(self, channels, out_channels, use_xyz=True):
         super().__init__()
         self.transfer = _ConvBNAct((3 if use_xyz else 0) + 2 * channels, out_channels)
         self.operation = nn.Sequential(_ConvBNActRes(out_channels))
-
-    def forward(self, x):
-        B, S, k, d = x.shape
-        y = self.operation(self.transfer(x.permute(0, 1, 3, 2).reshape(B * S, d, k)))
-        return y.amax(dim=-1).reshape(B, S, -1).permute(0, 2, 1)
 
 
 class LocalGrouper(nn.Module):
@@ -98,26 +90,15 @@ class LocalGrouper(nn.Module):
         self.extraction = _PreExtraction(in_channels, in_channels)
 
     def forward(self, xyz, feature, groups, k):
-        """xyz [B,3,N], feature [B,D,N] -> (new_xyz [B,3,S], new_feature [B,D,S])."""
-        pts = xyz.transpose(1, 2)
-        fea = feature.transpose(1, 2)
-        B = pts.shape[0]
+        """xyz [B,3,N], feature [B,D,N] -> (new_xyz [B,3,S], new_feature [B,D,S]); eval mode only (folded BatchNorm)."""
+        from . import grouping
+        if self.training:
+            raise RuntimeError("ldt_b200.LocalGrouper is an inference path: call .eval() (BatchNorm is folded into the weights)")
+        B = xyz.shape[0]
         with torch.no_grad():
-            new_xyz, fps_idx, idx = cluster(pts, groups, k)
-        anchor_fea = gather_points(fea, fps_idx)                       # [B,S,D]
-        grouped = gather_points(fea, idx)                              # [B,S,k,D]
-        if self.use_xyz:
-            grouped = torch.cat([grouped, gather_points(pts, idx)], dim=-1)
-        if self.normalize is not None:
-            if self.normalize == "center":
-                mean = grouped.mean(dim=2, keepdim=True)
-            else:
-                mean = (torch.cat([anchor_fea, new_xyz], dim=-1) if self.use_xyz else anchor_fea).unsqueeze(-2)
-            centred = grouped - mean
-            std = torch.std(centred.reshape(B, -1), dim=-1, keepdim=True)[:, :, None, None]
-            grouped = self.affine_alpha * (centred / (std + 1e-5)) + self.affine_beta
-        x = torch.cat([grouped, anchor_fea.unsqueeze(2).expand(-1, -1, k, -1)], dim=-1)
-        return new_xyz.transpose(1, 2), self.extraction(x)
+            packed = grouping.pack_grouper(self)
+            new_xyz, x = grouping.local_group(self, packed, self.normalize, xyz.transpose(1, 2), feature.transpose(1, 2), groups, k)
+        return new_xyz.transpose(1, 2), x.reshape(B, groups, -1).permute(0, 2, 1)
 
 
 class ConditionNet(nn.Module):
@@ -147,8 +128,14 @@ class ConditionNet(nn.Module):
             img = condition["img"].to(dev)
             img_cond = self.ln(F.adaptive_max_pool2d(self.resnet(img), 1).squeeze())
         if "pts" in condition and self.pt_condition:
-            pts = condition["pts"].to(dev).transpose(1, 2)
-            x = self.pc_conv_in(pts)
-            _, x = self.group(pts, x, self.patch_size, x.shape[1] // self.patch_size * 2)
-            pts_cond = self.pc_conv_out(x)
+            from . import grouping
+            pts = condition["pts"].to(dev).float().contiguous()            # [B, N, 3]
+            B, N = pts.shape[0], pts.shape[1]
+            with torch.no_grad():
+                x = grouping.conv_rows(pts.reshape(B * N, 3), grouping.pack_tf32(self.pc_conv_in))
+                k = x.shape[1] // self.patch_size * 2                          # score.py:40
+                _, x = grouping.local_group(self.group, grouping.pack_grouper(self.group), self.group.normalize, pts,
+                                            x.reshape(B, N, -1), self.patch_size, k)
+                x = grouping.conv_rows(x, grouping.pack_tf32(self.pc_conv_out))   # [B*S, hidden]
+            pts_cond = x.reshape(B, self.patch_size, -1).permute(0, 2, 1)   # [B, hidden, S] as the reference returns it
         return pts_cond, img_cond

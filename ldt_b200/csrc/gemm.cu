@@ -853,9 +853,19 @@ extern "C" int ldt_gemm_bf16(const ldt_gemm_args* args, void* stream) {
   p.dbg = g_gemm_dbg;
   p.dbg_mode = g_gemm_dbg_mode;
   p.tma_store = (g_gemm_dbg_mode & 256) ? 0 : 1;
+  p.relu = 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int epilogue = a.epilogue;
+  if (epilogue == LDT_EPI_BIAS_RELU_F32) {   // the same kernels as the plain f32 epilogues, ReLU as a run-time flag
+    epilogue = LDT_EPI_BIAS_F32;
+    p.relu = 1;
+  } else if (epilogue == LDT_EPI_RESID_RELU_F32) {
+    LDT_REQUIRE(a.gate == nullptr, LDT_ERR_INVALID, "ldt_gemm_bf16: LDT_EPI_RESID_RELU_F32 takes no gate");
+    epilogue = LDT_EPI_GATE_RESID_F32;
+    p.relu = 1;
+  }
   if (tf32) {
-    switch (a.epilogue) {
+    switch (epilogue) {
       case LDT_EPI_BIAS_F32: return launch_any_tf32<LDT_EPI_BIAS_F32>(a, p, s);
       case LDT_EPI_BIAS_GELU_F32: return launch_any_tf32<LDT_EPI_BIAS_GELU_F32>(a, p, s);
       case LDT_EPI_GATE_RESID_F32:
@@ -863,12 +873,12 @@ extern "C" int ldt_gemm_bf16(const ldt_gemm_args* args, void* stream) {
         LDT_REQUIRE(a.gate == nullptr || a.gate_stride % 4 == 0, LDT_ERR_INVALID, "ldt_gemm_bf16: gate_stride must be a multiple of 4");
         return launch_any_tf32<LDT_EPI_GATE_RESID_F32>(a, p, s);
       default:
-        set_last_error("ldt_gemm_bf16: epilogue %d is not available for f32 operands (0, 3, 4 are)", a.epilogue);
+        set_last_error("ldt_gemm_bf16: epilogue %d is not available for f32 operands (0, 3, 4, 5, 6 are)", a.epilogue);
         return LDT_ERR_UNSUPPORTED;
     }
   }
   LDT_REQUIRE(a.epilogue != LDT_EPI_BIAS_GELU_F32, LDT_ERR_UNSUPPORTED, "ldt_gemm_bf16: LDT_EPI_BIAS_GELU_F32 needs operand_type 1");
-  switch (a.epilogue) {
+  switch (epilogue) {
     case LDT_EPI_BIAS_F32: return launch_any<LDT_EPI_BIAS_F32>(a, p, s);
     case LDT_EPI_BIAS_BF16: return launch_any<LDT_EPI_BIAS_BF16>(a, p, s);
     case LDT_EPI_BIAS_GELU_BF16: return launch_any<LDT_EPI_BIAS_GELU_BF16>(a, p, s);

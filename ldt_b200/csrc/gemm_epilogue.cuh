@@ -46,7 +46,10 @@ struct EpiParams {
   unsigned long long* dbg;  // optional per-CTA stall counters (ldt_debug_set_gemm_counters), else nullptr
   int tma_store;            // bf16 outputs leave through bulk tensor stores (0: per-lane st.global, kept for A/B and tests)
   int dbg_mode;             // experiments only (ldt_debug_set_gemm_mode): 1 skip A loads, 2 skip W loads, 4 skip the epilogue
+  int relu;                 // f32 outputs only: 1 = max(., 0) last (LDT_EPI_BIAS_RELU_F32 / LDT_EPI_RESID_RELU_F32)
 };
+
+__device__ __forceinline__ float epi_relu(float x, int) { return fmaxf(x, 0.f); }
 
 // One thread finishes 32 consecutive columns [col0, col0+32) of output row `row`.
 template <int EPI>
@@ -99,6 +102,12 @@ __device__ __forceinline__ void epilogue_row32(const EpiParams& p, int row, int 
     }
   }
   if constexpr (EPI == LDT_EPI_BIAS_F32 || EPI == LDT_EPI_GATE_RESID_F32 || EPI == LDT_EPI_BIAS_GELU_F32) {
+    if constexpr (EPI != LDT_EPI_BIAS_GELU_F32) {
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = epi_relu(v[j], p.relu);
+      }
+    }
     float* o = static_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
     if (full) {
 #pragma unroll
@@ -214,6 +223,7 @@ __device__ __forceinline__ void epilogue_staged(const EpiParams& p, uint8_t* stg
       if (col < p.N && p.bias != nullptr) b4s[u] = __ldg(reinterpret_cast<const float4*>(p.bias + col));
     }
     // one load-add-store round: staged row rr0 + 4*i, 16-byte chunk cc -> bias, gate, residual -> global
+    const int relu = p.relu;
     auto finish = [&](float4 a4, const float4& g, const float4& b4, const float4& r) -> float4 {
 #ifdef LDT_EPI_SCALAR_F32   // A/B builds only
       a4.x += b4.x; a4.y += b4.y; a4.z += b4.z; a4.w += b4.w;
@@ -235,6 +245,8 @@ __device__ __forceinline__ void epilogue_staged(const EpiParams& p, uint8_t* stg
       if constexpr (EPI == LDT_EPI_BIAS_GELU_F32) {   // TF32 parity mode: exact-erf GELU, rounded to TF32
         a4.x = round_tf32(gelu_erf_f(a4.x)); a4.y = round_tf32(gelu_erf_f(a4.y));
         a4.z = round_tf32(gelu_erf_f(a4.z)); a4.w = round_tf32(gelu_erf_f(a4.w));
+      } else if (relu) {   // warp-uniform; the encoder prologue's Conv1d + BatchNorm + ReLU layers (LDT_EPI_*_RELU_F32)
+        a4.x = epi_relu(a4.x, relu); a4.y = epi_relu(a4.y, relu); a4.z = epi_relu(a4.z, relu); a4.w = epi_relu(a4.w, relu);
       }
       return a4;
     };

@@ -150,6 +150,115 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(int n, int s, int k, c
 
 using namespace ldt;
 
+
+// ------------------------------------------------------------------------------------------------
+// LocalGrouper's normalised group features (reference model/Compressor/layers.py:300-317), written directly as the A
+// operand [b*s*k, ld_out] of PreExtraction's first 1x1 convolution: for group (b, s) and neighbour j
+//     g      = cat(fea[b, idx[b,s,j], :], xyz[b, idx[b,s,j], :])                         d + 3 channels
+//     mean   = cat(fea[b, ci, :], xyz[b, ci, :])  ("anchor", ci = center_idx[b,s])   or   mean_j g  ("center")
+//     row    = cat(alpha * ((g - mean) / (std_b + 1e-5)) + beta,  fea[b, ci, :]),  zero-padded
+// with std_b the unbiased standard deviation of ALL (g - mean) of sample b (torch.std over reshape(B, -1)).  Two kernels:
+// per-group partial sums in double (fixed order, no atomics), then every block re-reduces its sample's s partials.
+// ------------------------------------------------------------------------------------------------
+constexpr int GRP_THREADS = 128;
+
+__device__ __forceinline__ float group_value(const float* __restrict__ xyz, const float* __restrict__ fea, int d, size_t point, int c) {
+  return c < d ? __ldg(fea + point * d + c) : __ldg(xyz + point * 3 + (c - d));
+}
+
+template <bool ASSEMBLE>
+__global__ void __launch_bounds__(GRP_THREADS)
+group_kernel(int n, int s_, int k, int d, const float* __restrict__ xyz, const float* __restrict__ fea,
+             const int* __restrict__ center_idx, const int* __restrict__ group_idx, int normalize,
+             const float* __restrict__ alpha, const float* __restrict__ beta, double* __restrict__ partial,
+             float* __restrict__ out, int ld_out) {
+  extern __shared__ int s_idx[];   // the group's k neighbour indices
+  __shared__ double red[2][GRP_THREADS];
+  __shared__ float s_denom;
+  const int s = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const size_t base = static_cast<size_t>(b) * n;
+  for (int j = tid; j < k; j += GRP_THREADS) s_idx[j] = group_idx[(static_cast<size_t>(b) * s_ + s) * k + j];
+  const size_t ci = base + center_idx[static_cast<size_t>(b) * s_ + s];
+  if (ASSEMBLE && tid == 0) {
+    float denom = 1.f;
+    if (normalize != 0) {
+      double S = 0.0, Q = 0.0;
+      for (int i = 0; i < s_; ++i) {
+        S += partial[(static_cast<size_t>(b) * s_ + i) * 2];
+        Q += partial[(static_cast<size_t>(b) * s_ + i) * 2 + 1];
+      }
+      const double cnt = static_cast<double>(s_) * k * (d + 3);
+      const double var = (Q - S * S / cnt) / (cnt - 1.0);
+      denom = __fadd_rn(static_cast<float>(sqrt(var > 0.0 ? var : 0.0)), 1e-5f);
+    }
+    s_denom = denom;
+  }
+  __syncthreads();
+  const int dc = d + 3;
+  double sum = 0.0, sq = 0.0;
+  for (int c = tid; c < dc; c += GRP_THREADS) {
+    float mean = 0.f;
+    if (normalize == 2) {
+      mean = group_value(xyz, fea, d, ci, c);
+    } else if (normalize == 1) {
+      float acc = 0.f;
+      for (int j = 0; j < k; ++j) acc += group_value(xyz, fea, d, base + s_idx[j], c);
+      mean = acc / static_cast<float>(k);
+    }
+    if constexpr (ASSEMBLE) {
+      const float denom = s_denom;
+      const float al = normalize != 0 ? __ldg(alpha + c) : 1.f, be = normalize != 0 ? __ldg(beta + c) : 0.f;
+      float* o = out + (static_cast<size_t>(b) * s_ + s) * k * ld_out + c;
+      for (int j = 0; j < k; ++j) {
+        float v = group_value(xyz, fea, d, base + s_idx[j], c);
+        if (normalize != 0) v = __fadd_rn(__fmul_rn(al, __fdiv_rn(__fsub_rn(v, mean), denom)), be);
+        o[static_cast<size_t>(j) * ld_out] = v;
+      }
+    } else {
+      for (int j = 0; j < k; ++j) {
+        const double v = static_cast<double>(__fsub_rn(group_value(xyz, fea, d, base + s_idx[j], c), mean));
+        sum += v;
+        sq += v * v;
+      }
+    }
+  }
+  if constexpr (ASSEMBLE) {
+    // the anchor's own feature repeated for every neighbour, then the zero padding
+    for (int c = dc + tid; c < ld_out; c += GRP_THREADS) {
+      const float v = c < dc + d ? __ldg(fea + ci * d + (c - dc)) : 0.f;
+      float* o = out + (static_cast<size_t>(b) * s_ + s) * k * ld_out + c;
+      for (int j = 0; j < k; ++j) o[static_cast<size_t>(j) * ld_out] = v;
+    }
+  } else {
+    red[0][tid] = sum;
+    red[1][tid] = sq;
+    __syncthreads();
+    for (int w = GRP_THREADS / 2; w > 0; w >>= 1) {
+      if (tid < w) {
+        red[0][tid] += red[0][tid + w];
+        red[1][tid] += red[1][tid + w];
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      partial[(static_cast<size_t>(b) * s_ + s) * 2] = red[0][0];
+      partial[(static_cast<size_t>(b) * s_ + s) * 2 + 1] = red[1][0];
+    }
+  }
+}
+
+// out[g, c] = max_j x[g*k + j, c]: the max over a group's neighbours that ends PreExtraction (layers.py:189-190) and
+// MiniPointnet's max over the centres (Network.py:97).
+__global__ void group_max_kernel(int k, int c_, const float* __restrict__ x, int ldx, float* __restrict__ out, int ldo) {
+  const size_t g = blockIdx.x;
+  for (int c = threadIdx.x; c < c_; c += blockDim.x) {
+    const float* px = x + g * k * ldx + c;
+    float m = px[0];
+    for (int j = 1; j < k; ++j) m = fmaxf(m, px[static_cast<size_t>(j) * ldx]);
+    out[g * ldo + c] = m;
+  }
+}
+
 extern "C" int ldt_furthest_point_sample(int b, int n, int m, const float* xyz, float min_sq_norm, int* idx, void* stream) {
   LDT_REQUIRE(b >= 0 && n > 0 && m > 0 && m <= n, LDT_ERR_INVALID, "ldt_furthest_point_sample: bad shape b=%d n=%d m=%d", b, n, m);
   LDT_REQUIRE(n <= 16 * FPS_THREADS, LDT_ERR_UNSUPPORTED, "ldt_furthest_point_sample: n=%d exceeds %d points per cloud", n,
@@ -172,6 +281,38 @@ extern "C" int ldt_knn_indices(int b, int n, int s, int k, const float* xyz, con
   if (b == 0) return LDT_OK;
   LDT_REQUIRE(xyz && centers && idx, LDT_ERR_INVALID, "ldt_knn_indices: null pointer");
   knn_kernel<<<b * s, KNN_THREADS, n * sizeof(float), static_cast<cudaStream_t>(stream)>>>(n, s, k, xyz, centers, idx);
+  LDT_CUDA_OK(cudaGetLastError());
+  return LDT_OK;
+}
+
+extern "C" int ldt_group_features(int b, int n, int s, int k, int d, const float* xyz, const float* fea, const int* center_idx,
+                                  const int* group_idx, int normalize, const float* alpha, const float* beta, double* partial,
+                                  float* out, int ld_out, void* stream) {
+  LDT_REQUIRE(b >= 0 && n > 0 && s > 0 && k > 0 && d > 0, LDT_ERR_INVALID, "ldt_group_features: bad shape b=%d n=%d s=%d k=%d d=%d", b, n,
+              s, k, d);
+  LDT_REQUIRE(normalize >= 0 && normalize <= 2, LDT_ERR_INVALID, "ldt_group_features: normalize=%d (0 none, 1 center, 2 anchor)", normalize);
+  LDT_REQUIRE(ld_out >= 2 * d + 3, LDT_ERR_INVALID, "ldt_group_features: ld_out=%d < 2 d + 3 = %d", ld_out, 2 * d + 3);
+  LDT_REQUIRE(k <= 8192 && s <= 65535 && b <= 65535, LDT_ERR_UNSUPPORTED, "ldt_group_features: k=%d s=%d b=%d out of range", k, s, b);
+  if (b == 0) return LDT_OK;
+  LDT_REQUIRE(xyz && fea && center_idx && group_idx && out, LDT_ERR_INVALID, "ldt_group_features: null pointer");
+  LDT_REQUIRE(normalize == 0 || (alpha && beta && partial), LDT_ERR_INVALID, "ldt_group_features: normalisation needs alpha, beta and the scratch");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = static_cast<size_t>(k) * sizeof(int);
+  if (normalize != 0)
+    group_kernel<false><<<dim3(s, b), GRP_THREADS, smem, st>>>(n, s, k, d, xyz, fea, center_idx, group_idx, normalize, alpha, beta, partial,
+                                                               out, ld_out);
+  group_kernel<true><<<dim3(s, b), GRP_THREADS, smem, st>>>(n, s, k, d, xyz, fea, center_idx, group_idx, normalize, alpha, beta, partial, out,
+                                                            ld_out);
+  LDT_CUDA_OK(cudaGetLastError());
+  return LDT_OK;
+}
+
+extern "C" int ldt_group_max(int groups, int k, int c, const float* x, int ldx, float* out, int ldo, void* stream) {
+  LDT_REQUIRE(groups >= 0 && k > 0 && c > 0 && ldx >= c && ldo >= c, LDT_ERR_INVALID, "ldt_group_max: bad shape groups=%d k=%d c=%d ldx=%d ldo=%d",
+              groups, k, c, ldx, ldo);
+  if (groups == 0) return LDT_OK;
+  LDT_REQUIRE(x && out, LDT_ERR_INVALID, "ldt_group_max: null pointer");
+  group_max_kernel<<<groups, c < 256 ? ((c + 31) / 32) * 32 : 256, 0, static_cast<cudaStream_t>(stream)>>>(k, c, x, ldx, out, ldo);
   LDT_CUDA_OK(cudaGetLastError());
   return LDT_OK;
 }

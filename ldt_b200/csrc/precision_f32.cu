@@ -23,6 +23,26 @@ __global__ void __launch_bounds__(256) round_pad_tf32_kernel(long long rows, int
   }
 }
 
+// Error-compensated TF32 ("3xTF32"): v = hi + lo with hi = tf32(v), lo = tf32(v - hi) (v - hi is exact in fp32), so that
+//   a . w  ~=  a_hi . w_hi + a_hi . w_lo + a_lo . w_hi      (the dropped a_lo . w_lo term is ~2^-22 relative)
+// is ONE kind::tf32 contraction over 3 K: activations are laid out [hi | hi | lo], weights [hi | lo | hi], each part
+// ld_part columns wide (zero-padded).  fp32-grade results from the tensor cores for the small fp32 layers of the prologues.
+__global__ void __launch_bounds__(256) split_tf32_kernel(long long rows, int cols, const float* __restrict__ in, int ld_in,
+                                                       float* __restrict__ out, int ld_part, int weight_side) {
+  const long long total = rows * ld_part;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const long long r = i / ld_part;
+    const int c = static_cast<int>(i - r * ld_part);
+    const float v = (c < cols) ? in[r * ld_in + c] : 0.f;
+    const float hi = round_tf32(v);
+    const float lo = round_tf32(v - hi);
+    float* o = out + r * 3 * ld_part + c;
+    o[0] = hi;
+    o[ld_part] = weight_side ? lo : hi;
+    o[2 * ld_part] = weight_side ? hi : lo;
+  }
+}
+
 // LayerNorm(eps) over C channels (two-pass, as layernorm_mod_kernel), then AdaLN modulate or affine; f32 out, TF32-rounded.
 __global__ void __launch_bounds__(128) layernorm_mod_f32_kernel(int rows, int C, const float* __restrict__ x,
                                                               const float* __restrict__ shift, const float* __restrict__ scale,
@@ -122,6 +142,20 @@ extern "C" int ldt_round_pad_tf32(long long rows, int cols, const float* in, int
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (silu) round_pad_tf32_kernel<1><<<grid, 256, 0, s>>>(rows, cols, in, ld_in, out, ld_out);
   else round_pad_tf32_kernel<0><<<grid, 256, 0, s>>>(rows, cols, in, ld_in, out, ld_out);
+  LDT_CUDA_OK(cudaGetLastError());
+  return LDT_OK;
+}
+
+extern "C" int ldt_split_tf32(long long rows, int cols, const float* in, int ld_in, float* out, int ld_part, int weight_side,
+                              void* stream) {
+  LDT_REQUIRE(rows >= 0 && cols > 0 && ld_in >= cols && ld_part >= cols, LDT_ERR_INVALID,
+              "ldt_split_tf32: bad shape rows=%lld cols=%d ld_in=%d ld_part=%d", rows, cols, ld_in, ld_part);
+  if (rows == 0) return LDT_OK;
+  LDT_REQUIRE(in && out, LDT_ERR_INVALID, "ldt_split_tf32: null pointer");
+  const long long total = rows * ld_part;
+  const long long want = total / 256 + 1, cap = static_cast<long long>(num_sms()) * 16;
+  split_tf32_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, cols, in, ld_in, out,
+                                                                                                         ld_part, weight_side);
   LDT_CUDA_OK(cudaGetLastError());
   return LDT_OK;
 }

@@ -9,7 +9,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_BIAS_GELU_F32, EPI_GATE_RESID_F32, GemmArgs, MlpArgs, check, load,
+from ._lib import (EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_BIAS_GELU_F32, EPI_BIAS_RELU_F32, EPI_GATE_RESID_F32, EPI_RESID_RELU_F32, GemmArgs, MlpArgs, check, load,
                    ptr, stream_ptr)
 
 
@@ -308,6 +308,18 @@ def round_pad_tf32(x: torch.Tensor, ld_out: int | None = None, out: torch.Tensor
     return out
 
 
+def split_tf32(x: torch.Tensor, ld_part: int | None = None, weight_side: bool = False) -> torch.Tensor:
+    """f32 [rows, cols] -> f32 [rows, 3*ld_part], the error-compensated TF32 operand layout ("3xTF32"): activations
+    [hi | hi | lo], weights [hi | lo | hi]; one kind::tf32 contraction over 3*ld_part then has fp32-grade accuracy."""
+    _req(x, torch.float32, "x")
+    rows, cols = x.shape
+    ld_part = ((cols + 31) // 32) * 32 if ld_part is None else ld_part
+    out = torch.empty((rows, 3 * ld_part), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device), _launch("split_tf32"):
+        check(load().ldt_split_tf32(rows, cols, ptr(x), x.stride(0), ptr(out), ld_part, int(weight_side), stream_ptr()), "ldt_split_tf32")
+    return out
+
+
 def layernorm_mod_f32(x: torch.Tensor, out: torch.Tensor, *, shift=None, scale=None, mod_stride: int = 0,
                       rows_per_mod: int = 1, weight=None, bias=None, eps: float = 1e-6) -> torch.Tensor:
     rows, Cc = x.shape
@@ -430,6 +442,47 @@ def knn_indices(k: int, xyz: torch.Tensor, centers: torch.Tensor) -> torch.Tenso
     with torch.cuda.device(xyz.device), _launch("knn"):
         check(load().ldt_knn_indices(b, n, s, k, ptr(xyz), ptr(centers), ptr(idx), stream_ptr()), "ldt_knn_indices")
     return idx
+
+
+
+_NORMALIZE = {None: 0, "center": 1, "anchor": 2}
+
+
+def group_features(xyz: torch.Tensor, fea: torch.Tensor, center_idx: torch.Tensor, group_idx: torch.Tensor, normalize,
+                   alpha, beta, ld_out: int | None = None) -> torch.Tensor:
+    """LocalGrouper's normalised group features (model/Compressor/layers.py:300-317) as rows [b*s*k, ld_out] f32:
+    the A operand of PreExtraction's first 1x1 convolution.  xyz [b,n,3], fea [b,n,d] f32; center_idx [b,s], group_idx [b,s,k] i32."""
+    _req(xyz, torch.float32, "xyz")
+    _req(fea, torch.float32, "fea")
+    _req(center_idx, torch.int32, "center_idx")
+    _req(group_idx, torch.int32, "group_idx")
+    b, n, d = fea.shape
+    s, k = group_idx.shape[1], group_idx.shape[2]
+    if xyz.shape != (b, n, 3) or center_idx.shape != (b, s):
+        raise RuntimeError(f"group_features: inconsistent shapes {tuple(xyz.shape)} {tuple(fea.shape)} {tuple(center_idx.shape)} {tuple(group_idx.shape)}")
+    mode = _NORMALIZE[normalize]
+    ld_out = ((2 * d + 3 + 31) // 32) * 32 if ld_out is None else ld_out
+    out = torch.empty((b * s * k, ld_out), dtype=torch.float32, device=fea.device)
+    partial = torch.empty((b, s, 2), dtype=torch.float64, device=fea.device) if mode else None
+    if mode:
+        alpha = alpha.detach().reshape(-1).float().contiguous()
+        beta = beta.detach().reshape(-1).float().contiguous()
+    with torch.cuda.device(fea.device), _launch("group_features", 2 if mode else 1):
+        check(load().ldt_group_features(b, n, s, k, d, ptr(xyz), ptr(fea), ptr(center_idx), ptr(group_idx), mode,
+                                        ptr(alpha) if mode else None, ptr(beta) if mode else None, ptr(partial), ptr(out), ld_out,
+                                        stream_ptr()), "ldt_group_features")
+    return out
+
+
+def group_max(x: torch.Tensor, k: int, c: int | None = None) -> torch.Tensor:
+    """x f32 [groups*k, ldx] -> [groups, c]: max over each group's k rows."""
+    _req(x, torch.float32, "x")
+    c = x.shape[1] if c is None else c
+    groups = x.shape[0] // k
+    out = torch.empty((groups, c), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device), _launch("group_max"):
+        check(load().ldt_group_max(groups, k, c, ptr(x), x.stride(0), ptr(out), out.stride(0), stream_ptr()), "ldt_group_max")
+    return out
 
 
 __all__ = [n for n in dir() if not n.startswith("_")] + ["_lib"]

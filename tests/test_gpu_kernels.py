@@ -372,6 +372,80 @@ def test_gemm_tf32_operands(dev, M, N, K):
         ops.gemm(A, W, bias, torch.empty((M, ldo), dtype=torch.bfloat16, device=dev), 1, N=N, K=K)   # no bf16 epilogue for f32 operands
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 128, 259), (4096, 128, 128), (64, 256, 3), (2, 256, 256), (8192, 1024, 128)])
+def test_split_tf32_contraction_is_fp32_grade_with_relu_epilogues(dev, M, N, K):
+    """"3xTF32": ldt_split_tf32 lays activations out as [hi | hi | lo] and weights as [hi | lo | hi]; one kind::tf32
+    contraction over 3 K then reproduces the fp32 product to ~1e-5 (plain TF32: ~8e-4), which is what lets the fp32
+    Conv1d / Linear layers of the encoder and condition prologues run on the tensor cores.  Also the two ReLU epilogues
+    (Conv + BatchNorm + ReLU, ConvBNReLURes1D's residual form) and the bit pattern of the split itself."""
+    g = torch.Generator().manual_seed(M * 7 + N + K)
+    A = (torch.randn((M, K), generator=g) * 0.7).to(dev)
+    W = (torch.randn((N, K), generator=g) / K ** 0.5).to(dev)
+    bias = torch.randn((N,), generator=g).to(dev)
+    ld = (K + 31) // 32 * 32
+    A3, W3 = ops.split_tf32(A), ops.split_tf32(W, weight_side=True)
+    assert A3.shape == (M, 3 * ld) and W3.shape == (N, 3 * ld)
+    hi = O.tf32_round(A.cpu())
+    lo = O.tf32_round(A.cpu() - hi)
+    assert torch.equal(A3[:, :K].cpu(), hi) and torch.equal(A3[:, ld:ld + K].cpu(), hi) and torch.equal(A3[:, 2 * ld:2 * ld + K].cpu(), lo)
+    assert torch.all(A3[:, K:ld] == 0) and torch.all(A3[:, 2 * ld + K:] == 0)
+    whi = O.tf32_round(W.cpu())
+    assert torch.equal(W3[:, ld:ld + K].cpu(), O.tf32_round(W.cpu() - whi)) and torch.equal(W3[:, 2 * ld:2 * ld + K].cpu(), whi)
+    acc = A.double() @ W.double().t() + bias.double()
+    out = torch.empty((M, N), device=dev)
+    ops.gemm(A3, W3, bias, out, 0)
+    e3 = rel_rms_err(out, acc)
+    ops.gemm(ops.round_pad_tf32(A, ld), ops.round_pad_tf32(W, ld), bias, out, 0)
+    e1 = rel_rms_err(out, acc)
+    # the floor is the tensor core's fp32 accumulation (~7e-6 on exact products, test_gemm_tf32_operands), not the operands
+    assert e3 < 2e-5 and (K < 32 or e3 < e1 / 30), (e3, e1)
+    ops.gemm(A3, W3, bias, out, 5)                                   # LDT_EPI_BIAS_RELU_F32
+    assert torch.all(out >= 0) and rel_rms_err(out, acc.clamp_min(0)) < 2e-5
+    resid = torch.randn((M, N), generator=g).to(dev)
+    out = resid.clone()
+    ops.gemm(A3, W3, bias, out, 6, resid=out)                        # LDT_EPI_RESID_RELU_F32, in place
+    assert torch.all(out >= 0) and rel_rms_err(out, (acc + resid.double()).clamp_min(0)) < 2e-5
+    with pytest.raises(RuntimeError):
+        ops.gemm(A3, W3, bias, out, 6, resid=out, gate=bias)         # the ReLU residual form takes no gate
+
+
+@pytest.mark.parametrize("normalize", ["anchor", "center", None])
+def test_group_features_and_group_max_vs_torch_expression(dev, normalize):
+    """ldt_group_features == LocalGrouper's gather / normalise / affine / concatenate (model/Compressor/layers.py:300-317)
+    written out in torch on the same indices; ldt_group_max == amax over the neighbours."""
+    g = torch.Generator().manual_seed(5)
+    B, N, D, S, k = 3, 500, 128, 32, 24
+    xyz = torch.randn((B, N, 3), generator=g).to(dev)
+    fea = torch.randn((B, N, D), generator=g).to(dev)
+    ci = torch.stack([torch.randperm(N, generator=g)[:S] for _ in range(B)]).int().to(dev)
+    gi = torch.randint(0, N, (B, S, k), generator=g).int().to(dev)
+    alpha = (torch.rand((1, 1, 1, D + 3), generator=g) + 0.5).to(dev)
+    beta = torch.randn((1, 1, 1, D + 3), generator=g).to(dev)
+    rows = ops.group_features(xyz, fea, ci, gi, normalize, alpha, beta)
+    ld = rows.shape[1]
+    assert ld == 288 and rows.shape[0] == B * S * k
+
+    def take(p, idx):
+        flat = idx.reshape(B, -1).long()
+        return torch.gather(p, 1, flat.unsqueeze(-1).expand(-1, -1, p.shape[-1])).reshape(*idx.shape, p.shape[-1])
+    anchor = take(fea, ci)
+    grouped = torch.cat([take(fea, gi), take(xyz, gi)], dim=-1)
+    if normalize is not None:
+        mean = grouped.mean(dim=2, keepdim=True) if normalize == "center" else torch.cat([anchor, take(xyz, ci)], dim=-1).unsqueeze(-2)
+        centred = grouped - mean
+        std = torch.std(centred.reshape(B, -1), dim=-1, keepdim=True)[:, :, None, None]
+        grouped = alpha * (centred / (std + 1e-5)) + beta
+    ref = torch.cat([grouped, anchor.unsqueeze(2).expand(-1, -1, k, -1)], dim=-1).reshape(B * S * k, 2 * D + 3)
+    assert torch.all(rows[:, 2 * D + 3:] == 0)
+    assert torch.allclose(rows[:, :2 * D + 3], ref, rtol=2e-5, atol=2e-6), (rows[:, :2 * D + 3] - ref).abs().max()
+    if normalize is None:
+        assert torch.equal(rows[:, :2 * D + 3], ref)                 # pure gather + concatenate
+    again = ops.group_features(xyz, fea, ci, gi, normalize, alpha, beta)
+    assert torch.equal(rows, again)                                  # fixed-order sums: deterministic
+    mx = ops.group_max(rows, k)
+    assert torch.equal(mx, rows.reshape(B * S, k, ld).amax(dim=1))
+
+
 def test_gemm_tcgen05_matches_cross_check_bitwise_on_exact_inputs(dev):
     """Small-integer inputs make every product and partial sum exact, so tcgen05, the SIMT cross-check and fp64
     must agree to the bit: catches descriptor / swizzle / K-advance mistakes that tolerance tests can hide."""

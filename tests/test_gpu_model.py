@@ -769,6 +769,76 @@ def test_compressor_forward_vs_reference_golden(dev):
     assert rms_rel_err(out["all_eps"], emu["all_eps"]) < 2e-2, rms_rel_err(out["all_eps"], emu["all_eps"])
 
 
+@pytest.mark.parametrize("pre_group,norm", [(False, "anchor"), (True, "center")])
+def test_encoder_prologue_on_own_kernels_vs_fp32_torch_expression(dev, pre_group, norm):
+    """Network.py:189-199 (input Conv1d, LocalGrouper + PreExtraction with eval-mode BatchNorm, MiniPointnet, ActNorm) on the
+    library's kernels (3xTF32 contractions with folded BatchNorm and ReLU epilogues, ldt_group_features, ldt_group_max)
+    against the same layers written out with torch fp32 functional ops (TF32 off) on the same FPS / k-NN indices.
+    BatchNorm statistics and affine parameters are randomised so that the folding is actually exercised."""
+    import torch.nn.functional as F
+    from ldt_b200.condition import cluster, gather_points
+    c = airplane_config()
+    c["compressor"]["pre_group"] = pre_group
+    c["compressor"]["cluster_norm"] = norm
+    cfg = ns(c).compressor
+    comp, _ = build_compressor(cfg, 21, dev, gain=0.8)
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for name, t in list(comp.named_parameters()) + list(comp.named_buffers()):
+            if not name.startswith(("group.", "pre_grouper.", "pos_embedding.", "input.", "conv_in.")):
+                continue
+            if name.endswith(("running_var", "affine_alpha")) or (t.dim() == 1 and name.endswith(".weight")):
+                t.copy_(torch.rand(t.shape, generator=g) + 0.5)          # BatchNorm variance / scale, grouper alpha
+            elif name.endswith(("running_mean", "affine_beta", "shift", "log_scale")):
+                t.copy_(torch.randn(t.shape, generator=g) * 0.2)
+    B, N = 3, 2048
+    pts = torch.randn((B, N, 3), generator=g).to(dev) * 0.5
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            x, pos = comp.encoder_prologue(pts)
+
+            def bn(m, v):
+                return F.batch_norm(v, m.running_mean, m.running_var, m.weight, m.bias, training=False, eps=1e-5)
+
+            def group(gm, xyz, fea, groups, k):          # LocalGrouper.forward, Compressor/layers.py:288-319
+                new_xyz, fps_idx, idx = cluster(xyz, groups, k)
+                anchor = gather_points(fea, fps_idx)
+                grouped = torch.cat([gather_points(fea, idx), gather_points(xyz, idx)], dim=-1)
+                mean = grouped.mean(dim=2, keepdim=True) if norm == "center" else torch.cat([anchor, new_xyz], dim=-1).unsqueeze(-2)
+                centred = grouped - mean
+                std = torch.std(centred.reshape(B, -1), dim=-1, keepdim=True)[:, :, None, None]
+                grouped = gm.affine_alpha * (centred / (std + 1e-5)) + gm.affine_beta
+                v = torch.cat([grouped, anchor.unsqueeze(2).expand(-1, -1, k, -1)], dim=-1)
+                b, s_, kk, d = v.shape
+                v = v.permute(0, 1, 3, 2).reshape(b * s_, d, kk)
+                t = gm.extraction.transfer.net._modules
+                v = F.relu(bn(t["1"], F.conv1d(v, t["0"].weight, t["0"].bias)))
+                op = gm.extraction.operation._modules["0"]
+                y = F.relu(bn(op.net1._modules["1"], F.conv1d(v, op.net1._modules["0"].weight, op.net1._modules["0"].bias)))
+                v = F.relu(F.conv1d(y, op.net2._modules["0"].weight, op.net2._modules["0"].bias) + v)
+                return new_xyz, v.amax(dim=-1).reshape(b, s_, -1)
+
+            f = F.conv1d(pts.transpose(1, 2), comp.input.weight, comp.input.bias).transpose(1, 2)
+            xyz = pts
+            if pre_group:
+                xyz, f = group(comp.pre_grouper, xyz, f, 256, 32)
+            center, f = group(comp.group, xyz, f, 32, xyz.shape[1] // 32 * 2)
+            pe = comp.pos_embedding
+            y = F.relu(bn(pe.bn1, F.conv1d(center.transpose(1, 2), pe.conv1.weight, pe.conv1.bias)))
+            y = F.relu(bn(pe.bn2, F.conv1d(y, pe.conv2.weight, pe.conv2.bias)))
+            pos_ref = F.linear(y.amax(dim=2), pe.fc.weight, pe.fc.bias)
+            x_ref = (f - comp.conv_in.shift) * torch.exp(-comp.conv_in.log_scale)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert x.shape == x_ref.shape == (B, 32, cfg.hidden_dim) and pos.shape == pos_ref.shape == (B, cfg.p_dim)
+    # the 3xTF32 contraction drops only the lo.lo term (2^-22); what is left is the tensor core's fp32 accumulation
+    # (~1e-5 per contraction, three to five in a row) and the BatchNorm folding (W*s, (b-mean)*s+beta rounded once)
+    assert rel_rms_err(x, x_ref) < 1e-4, rel_rms_err(x, x_ref)
+    assert rel_rms_err(pos, pos_ref) < 1e-4, rel_rms_err(pos, pos_ref)
+
+
 @pytest.mark.parametrize("B,H,Nq,Nk,dh", [(2, 4, 32, 2048, 32), (3, 4, 32, 1000, 32), (1, 2, 5, 33, 32), (2, 4, 32, 700, 64)])
 def test_attention_longkv_vs_float64(dev, B, H, Nq, Nk, dh):
     from ldt_b200 import ops
