@@ -129,6 +129,8 @@ class ConditionNet(nn.Module):
             img_cond = self.ln(F.adaptive_max_pool2d(self.resnet(img), 1).squeeze())
         if "pts" in condition and self.pt_condition:
             from . import grouping
+            if self.group.training:
+                raise RuntimeError("ldt_b200.ConditionNet is an inference path: call .eval() (BatchNorm is folded into the weights)")
             pts = condition["pts"].to(dev).float().contiguous()            # [B, N, 3]
             B, N = pts.shape[0], pts.shape[1]
             with torch.no_grad():

@@ -58,6 +58,17 @@ def test_argument_validation_without_gpu():
     assert L.ldt_score_forward(None, None, None, 0, None, None) == -1
     assert L.ldt_sample_loop(None, None) == -1
     assert L.ldt_decoder_forward(None, None, None, None, None) == -1
+    assert L.ldt_group_features(2, 64, 4, 8, 16, None, None, None, None, 3, None, None, None, None, 64, None) == -1
+    assert b"normalize" in L.ldt_last_error_string()
+    assert L.ldt_group_features(2, 64, 4, 8, 16, None, None, None, None, 2, None, None, None, None, 32, None) == -1
+    assert b"ld_out" in L.ldt_last_error_string()
+    assert L.ldt_group_features(0, 64, 4, 8, 16, None, None, None, None, 0, None, None, None, None, 64, None) == 0
+    assert L.ldt_group_max(0, 8, 16, None, 16, None, 16, None) == 0 and L.ldt_group_max(4, 0, 16, None, 16, None, 16, None) == -1
+    assert L.ldt_split_tf32(4, 40, None, 40, None, 32, 0, None) == -1 and b"ld_part" in L.ldt_last_error_string()
+    a = _lib.GemmArgs(M=128, N=128, K=96, operand_type=1, epilogue=1)
+    a.lda = a.ldw = 96
+    a.ldo = 128
+    assert L.ldt_gemm_bf16(C.byref(a), None) < 0   # bf16 epilogues are not available to f32 operands (and operands are null)
 
 
 def test_state_dict_layout_matches_reference():
@@ -97,6 +108,28 @@ def test_config_validation_mirrors_reference_errors():
         sde.sample_discrete(None, 1, 10, "ancestral", "nope", 1, (32, 120), 1e-6, False, True, 0.01, "cpu")
     with pytest.raises(RuntimeError, match="CUDA"):   # no CPU fallback for the encoder path either
         Compressor(cfg.compressor).forward(torch.zeros(1, 64, 3))
+
+
+def test_batchnorm_folding_equals_conv_then_batchnorm_on_cpu():
+    """grouping.fold_conv_bn: Conv1d(k=1) followed by an eval-mode BatchNorm1d is one affine map (W*s, (b-mean)*s+beta); this
+    is what lets the prologue layers run as single contractions with a ReLU epilogue (Compressor/layers.py:115-160)."""
+    from ldt_b200.grouping import fold_conv_bn
+    torch.manual_seed(0)
+    conv, bn = torch.nn.Conv1d(37, 16, 1), torch.nn.BatchNorm1d(16)
+    with torch.no_grad():
+        bn.running_mean.normal_(0, 0.3)
+        bn.running_var.uniform_(0.5, 1.5)
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_(0, 0.2)
+    bn.eval()
+    x = torch.randn(5, 37, 11)
+    W, b = fold_conv_bn(conv, bn)
+    with torch.no_grad():
+        want = bn(conv(x))
+    got = torch.einsum("oc,bcn->bon", W, x) + b[None, :, None]
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
+    W0, b0 = fold_conv_bn(torch.nn.Linear(8, 4))
+    assert W0.shape == (4, 8) and b0.shape == (4,)
 
 
 def test_product_path_never_imports_oracle():
