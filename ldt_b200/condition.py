@@ -6,9 +6,10 @@ it is a prologue, not the hot loop.  What is B200-native here is the point-set p
 its un-vendored ``pointnet2_ops`` dependency: furthest point sampling and k-NN grouping are sm_100a kernels behind the
 C ABI (``ldt_furthest_point_sample``, ``ldt_knn_indices``), and the 1x1 convolutions with BatchNorm around them run as
 error-compensated kind::tf32 contractions of the library's GEMM core (``grouping.py``: fp32-grade "3xTF32", BatchNorm folded, ReLU / residual in the epilogue,
-``ldt_group_features`` / ``ldt_group_max``).  The ResNet18 stem on the image stays a torch / cuDNN module (SURVEY.md A10
-allows it: once per call, outside the loop).  The modules keep the reference's parameter names, so reference checkpoints
-load with ``strict=True``:
+``ldt_group_features`` / ``ldt_group_max``).  The ResNet18 stem + layer1 + layer2 on the image run the same way: im2col
+(``F.unfold``, a copy) + the 3xTF32 contraction with folded BatchNorm, ReLU and the BasicBlock residual in the epilogue, both
+max-pools on ``ldt_group_max`` -- no cuDNN on the path.  The modules keep the reference's parameter names, so reference
+checkpoints load with ``strict=True``:
 
   c_net.pc_conv_in, c_net.group.{affine_alpha, affine_beta, extraction.transfer.net.{0,1},
   extraction.operation.0.{net1.{0,1}, net2.0}}, c_net.pc_conv_out, c_net.resnet.{0,1,4,5}.*, c_net.ln, c_net.conv_out
@@ -17,7 +18,6 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import ops
 
@@ -125,8 +125,15 @@ class ConditionNet(nn.Module):
             raise RuntimeError("ldt_b200.ConditionNet runs on CUDA only (FPS / k-NN kernels have no CPU fallback)")
         pts_cond, img_cond = 0.0, 0.0
         if "img" in condition and self.img_condition:
+            from . import grouping
+            if self.resnet.training:
+                raise RuntimeError("ldt_b200.ConditionNet is an inference path: call .eval() (BatchNorm is folded into the weights)")
             img = condition["img"].to(dev)
-            img_cond = self.ln(F.adaptive_max_pool2d(self.resnet(img), 1).squeeze())
+            with torch.no_grad():
+                pooled = grouping.resnet_trunk_maxpool(self.resnet, img)             # adaptive_max_pool2d(resnet(img), 1)
+                img_cond = grouping.conv_rows(pooled, grouping.pack_tf32(self.ln))    # self.ln(...)
+            if img_cond.shape[0] == 1:
+                img_cond = img_cond.squeeze(0)                                        # the reference's .squeeze()  score.py:35
         if "pts" in condition and self.pt_condition:
             from . import grouping
             if self.group.training:

@@ -13,6 +13,7 @@ over neighbours ``ldt_group_max``.  torch only allocates.
 from __future__ import annotations
 
 import torch
+import torch.nn.functional as F
 
 from . import ops
 from ._lib import EPI_BIAS_F32, EPI_BIAS_RELU_F32, EPI_RESID_RELU_F32
@@ -91,3 +92,57 @@ def mini_pointnet(packed: dict, center: torch.Tensor) -> torch.Tensor:
     x = conv_rows(x, packed["conv2"], EPI_BIAS_RELU_F32)
     x = ops.group_max(x, S)                                               # torch.max(x, 2)
     return conv_rows(x, packed["fc"], EPI_BIAS_F32)
+
+
+# ------------------------------------------------------------------------------------------------
+# ConditionNet's image branch (model/scorenet/score.py:24-26,33-35): torchvision ResNet18 stem + layer1 + layer2, global
+# max-pool, Linear.  Every convolution is im2col (F.unfold: a copy, no arithmetic) followed by the same 3xTF32 contraction
+# with the eval-mode BatchNorm folded in and ReLU / the BasicBlock's residual in the epilogue; both max-pools are
+# ldt_group_max.  Activations are kept as channels-last rows [B*H*W, C].
+# ------------------------------------------------------------------------------------------------
+def _conv2d_rows(rows, shape, conv, bn, epilogue, resid=None):
+    """rows [B*H*W, C] (+ shape (B, H, W)) -> rows [B*Ho*Wo, Cout] and (B, Ho, Wo) for one Conv2d + BatchNorm2d."""
+    B, H, W = shape
+    x = rows.reshape(B, H, W, -1).permute(0, 3, 1, 2)
+    kh, kw = conv.kernel_size
+    (sh, sw), (ph, pw) = conv.stride, conv.padding
+    if conv.groups != 1 or conv.dilation != (1, 1):
+        raise NotImplementedError("ldt_b200: grouped / dilated Conv2d is not supported")
+    Ho, Wo = (H + 2 * ph - kh) // sh + 1, (W + 2 * pw - kw) // sw + 1
+    cols = F.unfold(x, (kh, kw), padding=(ph, pw), stride=(sh, sw))            # [B, C*kh*kw, Ho*Wo], (C, kh, kw) order
+    a = cols.transpose(1, 2).reshape(B * Ho * Wo, -1).contiguous()
+    return conv_rows(a, pack_tf32(conv, bn), epilogue, resid=resid), (B, Ho, Wo)
+
+
+def _maxpool2d_rows(rows, shape, pool):
+    """nn.MaxPool2d on non-negative rows (after a ReLU, so F.unfold's zero padding never wins over a real element)."""
+    B, H, W = shape
+    k, s, p = pool.kernel_size, pool.stride, pool.padding
+    C_ = rows.shape[1]
+    x = rows.reshape(B, H, W, C_).permute(0, 3, 1, 2)
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    cols = F.unfold(x, k, padding=p, stride=s).reshape(B, C_, k * k, Ho * Wo)   # window elements of every channel
+    a = cols.permute(0, 3, 2, 1).reshape(B * Ho * Wo * k * k, C_).contiguous()
+    return ops.group_max(a, k * k), (B, Ho, Wo)
+
+
+def _basic_block_rows(rows, shape, blk):
+    """torchvision BasicBlock: relu(bn2(conv2(relu(bn1(conv1(x))))) + (downsample(x) | x))."""
+    y, shp = _conv2d_rows(rows, shape, blk.conv1, blk.bn1, EPI_BIAS_RELU_F32)
+    identity = rows
+    if blk.downsample is not None:
+        identity, _ = _conv2d_rows(rows, shape, blk.downsample[0], blk.downsample[1], EPI_BIAS_F32)
+    return _conv2d_rows(y, shp, blk.conv2, blk.bn2, EPI_RESID_RELU_F32, resid=identity)
+
+
+def resnet_trunk_maxpool(trunk, img: torch.Tensor) -> torch.Tensor:
+    """``adaptive_max_pool2d(trunk(img), 1)`` for trunk = Sequential(conv1, bn1, relu, maxpool, layer1, layer2):
+    img [B,3,H,W] -> [B, 128] f32."""
+    conv1, bn1, _, pool, layer1, layer2 = list(trunk.children())
+    B, _, H, W = img.shape
+    rows = img.float().permute(0, 2, 3, 1).reshape(B * H * W, -1).contiguous()
+    rows, shp = _conv2d_rows(rows, (B, H, W), conv1, bn1, EPI_BIAS_RELU_F32)
+    rows, shp = _maxpool2d_rows(rows, shp, pool)
+    for blk in list(layer1) + list(layer2):
+        rows, shp = _basic_block_rows(rows, shp, blk)
+    return ops.group_max(rows, shp[1] * shp[2])

@@ -132,6 +132,42 @@ def test_batchnorm_folding_equals_conv_then_batchnorm_on_cpu():
     assert W0.shape == (4, 8) and b0.shape == (4,)
 
 
+def test_resnet_trunk_im2col_wiring_on_cpu(monkeypatch):
+    """grouping.resnet_trunk_maxpool (ConditionNet's image branch, scorenet/score.py:24-26,33-35): im2col ordering, stride /
+    padding arithmetic, the max-pool by unfold and the BasicBlock residual wiring, with the two device kernels stood in by
+    their torch definitions (the kernels themselves are checked on the GPU against the reference golden)."""
+    from torchvision import models
+    from ldt_b200 import grouping, ops
+    from ldt_b200._lib import EPI_BIAS_F32, EPI_BIAS_RELU_F32, EPI_RESID_RELU_F32
+    torch.manual_seed(1)
+    trunk = torch.nn.Sequential(*list(models.resnet18(weights=None).children())[:-4])
+    with torch.no_grad():
+        for m in trunk.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.2)
+                m.running_var.uniform_(0.5, 1.5)
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.normal_(0, 0.2)
+    trunk.eval()
+
+    def conv_rows(x, packed, epilogue=EPI_BIAS_F32, resid=None):
+        W, b = packed
+        y = x.double() @ W.double().t() + b.double()
+        if epilogue == EPI_RESID_RELU_F32:
+            y = y + resid.double()
+        if epilogue in (EPI_BIAS_RELU_F32, EPI_RESID_RELU_F32):
+            y = y.clamp_min(0)
+        return y.float()
+    monkeypatch.setattr(grouping, "pack_tf32", grouping.fold_conv_bn)
+    monkeypatch.setattr(grouping, "conv_rows", conv_rows)
+    monkeypatch.setattr(ops, "group_max", lambda x, k, c=None: x.reshape(x.shape[0] // k, k, x.shape[1]).amax(dim=1))
+    img = torch.rand(2, 3, 64, 96)
+    with torch.no_grad():
+        want = torch.nn.functional.adaptive_max_pool2d(trunk(img), 1).reshape(2, 128)
+        got = grouping.resnet_trunk_maxpool(trunk, img)
+    assert got.shape == (2, 128) and torch.allclose(got, want, rtol=1e-4, atol=1e-5), (got - want).abs().max()
+
+
 def test_product_path_never_imports_oracle():
     """The oracle is test infrastructure: nothing under ldt_b200/ may import or reference it."""
     for dirpath, _, files in os.walk(os.path.join(ROOT, "ldt_b200")):

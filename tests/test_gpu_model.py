@@ -540,7 +540,8 @@ def test_sample_then_decode_end_to_end_small_steps(dev):
 # completion path (BASELINE configs[4])
 # ------------------------------------------------------------------------------------------------
 def test_condition_net_and_conditional_score_vs_reference_golden(dev):
-    """Score(condition=True): the ConditionNet prologue (FPS + k-NN kernels, torch layers) against the reference's
+    """Score(condition=True): the ConditionNet prologue (FPS / k-NN / grouping kernels, 3xTF32 contractions incl. the ResNet
+    trunk by im2col) against the reference's
     own outputs, then the conditional forward called with the raw {'img','pts'} dict as the reference allows."""
     from tests.helpers import small_cond_score_cfg
     cfg = small_cond_score_cfg()
