@@ -51,7 +51,9 @@ def launches(path):
 
 
 def main():
-    rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    if len(sys.argv) < 2:
+        sys.exit(__doc__)
+    rnd = sys.argv[1]
     tag = ("_" + sys.argv[2]) if len(sys.argv) > 2 else ""
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     lp = os.path.join(OUT, "launches.csv")
