@@ -783,6 +783,32 @@ def test_fps_bit_exact_vs_oracle(dev, b, n, m, rule):
     assert torch.equal(got.cpu().long(), oracle_fps(x, m, rule))
 
 
+@pytest.mark.parametrize("b,n,m", [(4, 2048, 32), (3, 2048, 256), (2, 1000, 100), (2, 4000, 64), (5, 257, 257)])
+def test_fps_bit_exact_vs_reference_in_tree_cuda_kernel(dev, b, n, m):
+    """The reference's OWN furthest-point-sampling kernel (model/functional/src/sampling/sampling.cu:86-167, compiled from the
+    source where it lies into oracle/_ref/libref_fps.so) run on the same GPU: identical index sequences.  That kernel has
+    no small-norm skip rule, which is ldt_furthest_point_sample with min_sq_norm < 0; it reads channels-first [b,3,n]
+    coordinates and a distance scratch initialised to 1e38 (sampling.cpp:52-53).  n = 4000 crosses its 3072-point shared
+    buffer.  Exact distance ties (duplicate points) are the one documented difference and do not occur in these clouds."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_fps.so")
+    assert os.path.exists(path), "oracle/_ref/libref_fps.so missing: run `make -C oracle` in the build container"
+    R = C.CDLL(path)
+    fn = getattr(R, "_Z23furthest_point_samplingiiiPKfPfPi")   # furthest_point_sampling(b, n, m, coords, distances, indices)
+    fn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    fn.restype = None
+    g = torch.Generator().manual_seed(b * 1000 + n + m)
+    xyz = torch.randn((b, n, 3), generator=g).to(dev)
+    coords = xyz.transpose(1, 2).contiguous()
+    dist = torch.full((b, n), 1e38, device=dev)
+    want = torch.zeros((b, m), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    fn(b, n, m, coords.data_ptr(), dist.data_ptr(), want.data_ptr())   # legacy default stream
+    torch.cuda.synchronize()
+    got = ops.furthest_point_sample(xyz, m, -1.0)
+    assert torch.equal(got, want), (got != want).nonzero()[:4]
+    assert int(want[:, 0].abs().max()) == 0 and len(set(want[0].tolist())) == m
+
+
 def test_fps_rejects_bad_inputs(dev):
     x = torch.randn((2, 64, 3), device=dev)
     with pytest.raises(RuntimeError):
