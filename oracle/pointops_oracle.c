@@ -4,8 +4,10 @@
  * (model/Compressor/layers.py:106; completion_trainer/Latent_SDE_Trainer.py:182-183).  The dependency itself
  * (pointnet2_ops, README.md:22-24, no version pin) is NOT under /root/reference, so this restates its published
  * algorithm (erikwijmans/Pointnet2_PyTorch sampling_gpu.cu: start at index 0, temp[k] = min(temp[k], |p_k - p_old|^2),
- * skip points with |p|^2 <= 1e-3, pick the arg-max) -- PARITY UNPINNED against that library; with min_sq_norm < 0 it
- * is the algorithm of the reference's in-tree model/functional/src/sampling/sampling.cu:86-167.  Exact ties (duplicate
+ * skip points with |p|^2 <= 1e-3, pick the arg-max) -- the skip rule is PARITY UNPINNED against that library; with
+ * min_sq_norm < 0 it is the algorithm of the reference's in-tree model/functional/src/sampling/sampling.cu:86-167, and that
+ * form IS pinned: the in-tree kernel is compiled into oracle/_ref/libref_fps.so (oracle/Makefile) and the product kernel
+ * reproduces its index sequences bit for bit on the GPU (tests/test_gpu_kernels.py).  Exact ties (duplicate
  * points) resolve to the lowest index here; the CUDA originals resolve them by thread layout.
  * Distances use fmaf(dz,dz,fmaf(dy,dy,dx*dx)), nvcc's default contraction of the reference expression.
  *

@@ -269,7 +269,8 @@ def _cond_shapes(cfg):
 
 def test_condition_net_oracle_matches_reference():
     """ConditionNet (ResNet18 trunk + FPS/kNN LocalGrouper) and the conditional score forward vs the reference run
-    (pointnet2_ops FPS replaced by the C oracle on both sides: that dependency is not vendored -> parity unpinned)."""
+    (pointnet2_ops FPS replaced by the C oracle on both sides: that dependency is not vendored; the algorithm is pinned to the
+    reference's in-tree FPS kernel on the GPU, pointnet2_ops' small-norm skip rule stays unpinned)."""
     from tests.helpers import oracle_fps, small_cond_score_cfg
     cfg = small_cond_score_cfg()
     g = golden("condition.npz")
