@@ -840,6 +840,37 @@ def test_encoder_prologue_on_own_kernels_vs_fp32_torch_expression(dev, pre_group
     assert rel_rms_err(pos, pos_ref) < 1e-4, rel_rms_err(pos, pos_ref)
 
 
+def test_resnet_trunk_on_own_kernels_vs_torchvision_fp32(dev):
+    """ConditionNet's image branch (scorenet/score.py:24-26,33-35): ResNet18 stem + layer1 + layer2 + global max-pool as im2col +
+    3xTF32 contractions with folded BatchNorm2d, ReLU / BasicBlock-residual epilogues and ldt_group_max, against the same
+    torchvision modules evaluated by torch in fp32 (TF32 off).  BatchNorm statistics randomised."""
+    from torchvision import models
+    from ldt_b200 import grouping
+    torch.manual_seed(2)
+    trunk = torch.nn.Sequential(*list(models.resnet18(weights=None).children())[:-4])
+    with torch.no_grad():
+        for m in trunk.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.2)
+                m.running_var.uniform_(0.5, 1.5)
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.normal_(0, 0.2)
+    trunk = trunk.to(dev).eval()
+    img = torch.rand(3, 3, 224, 224, device=dev)
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            want = torch.nn.functional.adaptive_max_pool2d(trunk(img), 1).reshape(3, 128)
+            got = grouping.resnet_trunk_maxpool(trunk, img)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert got.shape == (3, 128)
+    # ~1e-5 per contraction from the tensor core's fp32 accumulation, which truncates: the error is a small NEGATIVE bias that
+    # adds up over the nine contractions in a row (measured 1.05e-4; plain TF32 operands would give ~3e-3)
+    assert rel_rms_err(got, want) < 3e-4, rel_rms_err(got, want)
+
+
 @pytest.mark.parametrize("B,H,Nq,Nk,dh", [(2, 4, 32, 2048, 32), (3, 4, 32, 1000, 32), (1, 2, 5, 33, 32), (2, 4, 32, 700, 64)])
 def test_attention_longkv_vs_float64(dev, B, H, Nq, Nk, dh):
     from ldt_b200 import ops
