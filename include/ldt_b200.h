@@ -124,7 +124,9 @@ typedef struct ldt_gemm_args {
   int operand_type; /* 0 = A, W are bf16 (tcgen05 kind::f16; the product path);
                        1 = A, W are f32 holding TF32-rounded values (tcgen05 kind::tf32, same pipeline, CTA-pair kernel
                            only): the parity mode that matches the precision of the reference's own GPU arithmetic
-                           (cuDNN TF32 convolutions).  K a multiple of 32, lda / ldw multiples of 4; epilogues 0, 3, 4 */
+                           (cuDNN TF32 convolutions).  K a multiple of 32, lda / ldw multiples of 4; epilogues 0, 3, 4, 5, 6;
+                       2 = as 1 for operands laid out by ldt_split_tf32 (3xTF32, fp32-grade): LDT_EPI_BIAS_GELU_F32 then does
+                           NOT round its output (the consumer splits it again) */
 } ldt_gemm_args;
 
 int ldt_gemm_bf16(const ldt_gemm_args* args, void* stream);
@@ -210,8 +212,8 @@ int ldt_time_embedding(int R, int half, int D, const float* t, const float* freq
  * TF32 parity mode (Score.precision = "tf32"): fp32 activations, kind::tf32 contractions (ldt_gemm_bf16 with
  * operand_type 1) -- the precision of the reference's own GPU path (cuDNN TF32 convolutions).  Plain SIMT kernels.
  *   ldt_round_pad_tf32      out f32 [rows, ld_out] = tf32_round(silu ? SiLU(in) : in), zero-padded columns cols..ld_out
- *   ldt_layernorm_mod_f32   ldt_layernorm_mod_bf16 with a TF32-rounded f32 output (any C)
- *   ldt_attention_nk32_f32  ldt_attention_nk32 on f32 q/k/v (dh in {32, 64}), fp32 softmax, TF32-rounded f32 output
+ *   ldt_layernorm_mod_f32   ldt_layernorm_mod_bf16 with an f32 output (any C), TF32-rounded when round_tf32_out != 0
+ *   ldt_attention_nk32_f32  ldt_attention_nk32 on f32 q/k/v (dh in {32, 64}), fp32 softmax, f32 output (rounded likewise)
  * ------------------------------------------------------------------------------------------------ */
 int ldt_round_pad_tf32(long long rows, int cols, const float* in, int ld_in, float* out, int ld_out, int silu, void* stream);
 
@@ -220,12 +222,16 @@ int ldt_round_pad_tf32(long long rows, int cols, const float* in, int ld_in, flo
  * weight row (weight_side = 1) [hi | lo | hi], each part zero-padded to ld_part columns, so that ONE ldt_gemm_bf16 call with
  * operand_type 1 and K = 3*ld_part computes a_hi.w_hi + a_hi.w_lo + a_lo.w_hi.  Used for the fp32 Conv1d / Linear layers of
  * the encoder and condition prologues (model/Compressor/Network.py:192, layers.py:115-160, scorenet/score.py:36-41), which
- * the reference evaluates in fp32. */
-int ldt_split_tf32(long long rows, int cols, const float* in, int ld_in, float* out, int ld_part, int weight_side, void* stream);
+ * the reference evaluates in fp32, and for Score.precision = "fp32" (the fp32-grade parity mode of the score net: the producers
+ * above then run with round_tf32_out = 0 and every contraction operand goes through this split; silu = 1 applies SiLU first,
+ * the adaLN input of layers.py:172). */
+int ldt_split_tf32(long long rows, int cols, const float* in, int ld_in, float* out, int ld_part, int weight_side, int silu,
+                   void* stream);
 int ldt_layernorm_mod_f32(int rows, int C, const float* x, const float* shift, const float* scale, long long mod_stride,
-                          int rows_per_mod, const float* weight, const float* bias, float eps, float* y, void* stream);
+                          int rows_per_mod, const float* weight, const float* bias, float eps, float* y, int round_tf32_out,
+                          void* stream);
 int ldt_attention_nk32_f32(int B, int H, int Nq, int dh, const float* q, int ldq, const float* k, const float* v, int ldkv,
-                           float* o, void* stream);
+                           float* o, int round_tf32_out, void* stream);
 
 /* Multi-head attention over a short key set, one (batch, head) pair per warp group.
  *   q  bf16 [B*Nq, ldq]  (head h uses columns h*dh..h*dh+dh-1 -- contiguous channel groups,

@@ -829,8 +829,8 @@ extern "C" int ldt_gemm_bf16(const ldt_gemm_args* args, void* stream) {
   LDT_REQUIRE(args != nullptr, LDT_ERR_INVALID, "ldt_gemm_bf16: null args");
   const ldt_gemm_args& a = *args;
   LDT_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, LDT_ERR_INVALID, "ldt_gemm_bf16: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
-  const bool tf32 = a.operand_type == 1;
-  LDT_REQUIRE(a.operand_type == 0 || a.operand_type == 1, LDT_ERR_INVALID, "ldt_gemm_bf16: unknown operand_type %d", a.operand_type);
+  const bool tf32 = a.operand_type == 1 || a.operand_type == 2;
+  LDT_REQUIRE(a.operand_type >= 0 && a.operand_type <= 2, LDT_ERR_INVALID, "ldt_gemm_bf16: unknown operand_type %d", a.operand_type);
   if (tf32) {
     LDT_REQUIRE(a.K % (TC_BK / 2) == 0, LDT_ERR_INVALID, "ldt_gemm_bf16: K=%d must be a multiple of %d for f32 operands", a.K, TC_BK / 2);
     LDT_REQUIRE(a.backend == 0 || a.backend == 3, LDT_ERR_UNSUPPORTED, "ldt_gemm_bf16: f32 operands run on the CTA-pair kernel only");
@@ -854,6 +854,7 @@ extern "C" int ldt_gemm_bf16(const ldt_gemm_args* args, void* stream) {
   p.dbg_mode = g_gemm_dbg_mode;
   p.tma_store = (g_gemm_dbg_mode & 256) ? 0 : 1;
   p.relu = 0;
+  p.f32_plain = a.operand_type == 2;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int epilogue = a.epilogue;
   if (epilogue == LDT_EPI_BIAS_RELU_F32) {   // the same kernels as the plain f32 epilogues, ReLU as a run-time flag

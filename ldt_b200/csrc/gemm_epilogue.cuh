@@ -46,6 +46,7 @@ struct EpiParams {
   unsigned long long* dbg;  // optional per-CTA stall counters (ldt_debug_set_gemm_counters), else nullptr
   int tma_store;            // bf16 outputs leave through bulk tensor stores (0: per-lane st.global, kept for A/B and tests)
   int dbg_mode;             // experiments only (ldt_debug_set_gemm_mode): 1 skip A loads, 2 skip W loads, 4 skip the epilogue
+  int f32_plain;            // LDT_EPI_BIAS_GELU_F32 only: 1 = do not round the output to TF32 (operand_type 2, the 3xTF32 mode)
   int relu;                 // f32 outputs only: 1 = max(., 0) last (LDT_EPI_BIAS_RELU_F32 / LDT_EPI_RESID_RELU_F32)
 };
 
@@ -78,7 +79,10 @@ __device__ __forceinline__ void epilogue_row32(const EpiParams& p, int row, int 
   }
   if constexpr (EPI == LDT_EPI_BIAS_GELU_F32) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = round_tf32(gelu_erf_f(v[j]));
+    for (int j = 0; j < 32; ++j) {
+      v[j] = gelu_erf_f(v[j]);
+      if (!p.f32_plain) v[j] = round_tf32(v[j]);
+    }
   }
   if constexpr (EPI == LDT_EPI_GATE_RESID_F32) {
     const float* res = p.resid + static_cast<size_t>(row) * p.ldo + col0;
@@ -243,8 +247,8 @@ __device__ __forceinline__ void epilogue_staged(const EpiParams& p, uint8_t* stg
       unpack_f32x2(hi, a4.z, a4.w);
 #endif
       if constexpr (EPI == LDT_EPI_BIAS_GELU_F32) {   // TF32 parity mode: exact-erf GELU, rounded to TF32
-        a4.x = round_tf32(gelu_erf_f(a4.x)); a4.y = round_tf32(gelu_erf_f(a4.y));
-        a4.z = round_tf32(gelu_erf_f(a4.z)); a4.w = round_tf32(gelu_erf_f(a4.w));
+        a4.x = gelu_erf_f(a4.x); a4.y = gelu_erf_f(a4.y); a4.z = gelu_erf_f(a4.z); a4.w = gelu_erf_f(a4.w);
+        if (!p.f32_plain) { a4.x = round_tf32(a4.x); a4.y = round_tf32(a4.y); a4.z = round_tf32(a4.z); a4.w = round_tf32(a4.w); }
       } else if (relu) {   // warp-uniform; the encoder prologue's Conv1d + BatchNorm + ReLU layers (LDT_EPI_*_RELU_F32)
         a4.x = epi_relu(a4.x, relu); a4.y = epi_relu(a4.y, relu); a4.z = epi_relu(a4.z, relu); a4.w = epi_relu(a4.w, relu);
       }

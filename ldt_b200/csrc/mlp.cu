@@ -373,10 +373,10 @@ extern "C" int ldt_mlp_bf16(const ldt_mlp_args* args, void* stream) {
 
   MlpParams p;
   p.e1.M = a.M; p.e1.N = a.inner; p.e1.bias = a.bias1; p.e1.out = a.hidden; p.e1.ldo = a.ldh;
-  p.e1.resid = nullptr; p.e1.gate = nullptr; p.e1.gate_stride = 0; p.e1.rows_per_gate = 1; p.e1.dbg = nullptr; p.e1.dbg_mode = 0; p.e1.relu = 0; p.e1.tma_store = (ldt_debug_get_gemm_mode() & 256) ? 0 : 1;
+  p.e1.resid = nullptr; p.e1.gate = nullptr; p.e1.gate_stride = 0; p.e1.rows_per_gate = 1; p.e1.dbg = nullptr; p.e1.dbg_mode = 0; p.e1.relu = 0; p.e1.f32_plain = 0; p.e1.tma_store = (ldt_debug_get_gemm_mode() & 256) ? 0 : 1;
   p.e2.M = a.M; p.e2.N = a.C; p.e2.bias = a.bias2; p.e2.out = a.out; p.e2.ldo = a.ldo;
   p.e2.resid = a.resid; p.e2.gate = a.gate; p.e2.gate_stride = a.gate_stride;
-  p.e2.rows_per_gate = a.rows_per_gate > 0 ? a.rows_per_gate : 1; p.e2.dbg = nullptr; p.e2.dbg_mode = 0; p.e2.relu = 0; p.e2.tma_store = 0;
+  p.e2.rows_per_gate = a.rows_per_gate > 0 ? a.rows_per_gate : 1; p.e2.dbg = nullptr; p.e2.dbg_mode = 0; p.e2.relu = 0; p.e2.f32_plain = 0; p.e2.tma_store = 0;
   p.sync = a.sync;
   p.ready_target = static_cast<unsigned int>(tn1 * 16);
   p.done_target = static_cast<unsigned int>(tn2 * 2);

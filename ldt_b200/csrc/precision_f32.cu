@@ -27,13 +27,15 @@ __global__ void __launch_bounds__(256) round_pad_tf32_kernel(long long rows, int
 //   a . w  ~=  a_hi . w_hi + a_hi . w_lo + a_lo . w_hi      (the dropped a_lo . w_lo term is ~2^-22 relative)
 // is ONE kind::tf32 contraction over 3 K: activations are laid out [hi | hi | lo], weights [hi | lo | hi], each part
 // ld_part columns wide (zero-padded).  fp32-grade results from the tensor cores for the small fp32 layers of the prologues.
+template <int ACT>
 __global__ void __launch_bounds__(256) split_tf32_kernel(long long rows, int cols, const float* __restrict__ in, int ld_in,
                                                        float* __restrict__ out, int ld_part, int weight_side) {
   const long long total = rows * ld_part;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
     const long long r = i / ld_part;
     const int c = static_cast<int>(i - r * ld_part);
-    const float v = (c < cols) ? in[r * ld_in + c] : 0.f;
+    float v = (c < cols) ? in[r * ld_in + c] : 0.f;
+    if (ACT == 1) v = silu_f(v);
     const float hi = round_tf32(v);
     const float lo = round_tf32(v - hi);
     float* o = out + r * 3 * ld_part + c;
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(128) layernorm_mod_f32_kernel(int rows, int C,
                                                               const float* __restrict__ shift, const float* __restrict__ scale,
                                                               long long mod_stride, int rows_per_mod,
                                                               const float* __restrict__ weight, const float* __restrict__ bias,
-                                                              float eps, float* __restrict__ y) {
+                                                              float eps, float* __restrict__ y, int round_out) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -74,7 +76,8 @@ __global__ void __launch_bounds__(128) layernorm_mod_f32_kernel(int rows, int C,
       if (weight) mu = weight[c];
       if (bias) ad = bias[c];
     }
-    yr[c] = round_tf32((xr[c] - mean) * rstd * mu + ad);
+    const float o = (xr[c] - mean) * rstd * mu + ad;
+    yr[c] = round_out ? round_tf32(o) : o;
   }
 }
 
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(128) layernorm_mod_f32_kernel(int rows, int C,
 template <int DH>
 __global__ void __launch_bounds__(64) attention_nk32_f32_kernel(int units, int H, int Nq, int qtiles, const float* __restrict__ q,
                                                                int ldq, const float* __restrict__ k, const float* __restrict__ v,
-                                                               int ldkv, float* __restrict__ o, float scale) {
+                                                               int ldkv, float* __restrict__ o, float scale, int round_out) {
   __shared__ float Ks[2][32][DH + 1], Vs[2][32][DH + 1];   // two warps per CTA: 33 KB at dh 64
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit = blockIdx.x * 2 + warp;
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(64) attention_nk32_f32_kernel(int units, int H
   const float inv = 1.0f / sum;
   float* op = o + ((static_cast<size_t>(b) * H + h) * Nq + qi) * DH;
 #pragma unroll
-  for (int d = 0; d < DH; ++d) op[d] = round_tf32(out[d] * inv);
+  for (int d = 0; d < DH; ++d) op[d] = round_out ? round_tf32(out[d] * inv) : out[d] * inv;
 }
 
 }  // namespace ldt
@@ -147,21 +150,24 @@ extern "C" int ldt_round_pad_tf32(long long rows, int cols, const float* in, int
 }
 
 extern "C" int ldt_split_tf32(long long rows, int cols, const float* in, int ld_in, float* out, int ld_part, int weight_side,
-                              void* stream) {
+                              int silu, void* stream) {
   LDT_REQUIRE(rows >= 0 && cols > 0 && ld_in >= cols && ld_part >= cols, LDT_ERR_INVALID,
               "ldt_split_tf32: bad shape rows=%lld cols=%d ld_in=%d ld_part=%d", rows, cols, ld_in, ld_part);
   if (rows == 0) return LDT_OK;
   LDT_REQUIRE(in && out, LDT_ERR_INVALID, "ldt_split_tf32: null pointer");
   const long long total = rows * ld_part;
   const long long want = total / 256 + 1, cap = static_cast<long long>(num_sms()) * 16;
-  split_tf32_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, cols, in, ld_in, out,
-                                                                                                         ld_part, weight_side);
+  const int grid = static_cast<int>(want < cap ? want : cap);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (silu) split_tf32_kernel<1><<<grid, 256, 0, st>>>(rows, cols, in, ld_in, out, ld_part, weight_side);
+  else split_tf32_kernel<0><<<grid, 256, 0, st>>>(rows, cols, in, ld_in, out, ld_part, weight_side);
   LDT_CUDA_OK(cudaGetLastError());
   return LDT_OK;
 }
 
 extern "C" int ldt_layernorm_mod_f32(int rows, int C, const float* x, const float* shift, const float* scale, long long mod_stride,
-                                     int rows_per_mod, const float* weight, const float* bias, float eps, float* y, void* stream) {
+                                     int rows_per_mod, const float* weight, const float* bias, float eps, float* y, int round_tf32_out,
+                                     void* stream) {
   LDT_REQUIRE(rows >= 0 && C > 0, LDT_ERR_INVALID, "ldt_layernorm_mod_f32: bad shape rows=%d C=%d", rows, C);
   if (rows == 0) return LDT_OK;
   LDT_REQUIRE(x && y, LDT_ERR_INVALID, "ldt_layernorm_mod_f32: null pointer");
@@ -169,13 +175,13 @@ extern "C" int ldt_layernorm_mod_f32(int rows, int C, const float* x, const floa
   LDT_REQUIRE(!(scale && weight), LDT_ERR_INVALID, "ldt_layernorm_mod_f32: pass AdaLN (shift,scale) or affine (weight,bias), not both");
   if (rows_per_mod <= 0) rows_per_mod = 1;
   layernorm_mod_f32_kernel<<<(rows + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(rows, C, x, shift, scale, mod_stride,
-                                                                                         rows_per_mod, weight, bias, eps, y);
+                                                                                         rows_per_mod, weight, bias, eps, y, round_tf32_out);
   LDT_CUDA_OK(cudaGetLastError());
   return LDT_OK;
 }
 
 extern "C" int ldt_attention_nk32_f32(int B, int H, int Nq, int dh, const float* q, int ldq, const float* k, const float* v, int ldkv,
-                                      float* o, void* stream) {
+                                      float* o, int round_tf32_out, void* stream) {
   LDT_REQUIRE(B >= 0 && H > 0 && Nq > 0, LDT_ERR_INVALID, "ldt_attention_nk32_f32: bad shape B=%d H=%d Nq=%d", B, H, Nq);
   LDT_REQUIRE(dh == 32 || dh == 64, LDT_ERR_UNSUPPORTED, "ldt_attention_nk32_f32: head dim %d not in {32, 64}", dh);
   if (B == 0) return LDT_OK;
@@ -187,8 +193,8 @@ extern "C" int ldt_attention_nk32_f32(int B, int H, int Nq, int dh, const float*
   const int grid = static_cast<int>((units + 1) / 2);
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (dh == 64) attention_nk32_f32_kernel<64><<<grid, 64, 0, s>>>(static_cast<int>(units), H, Nq, qtiles, q, ldq, k, v, ldkv, o, scale);
-  else attention_nk32_f32_kernel<32><<<grid, 64, 0, s>>>(static_cast<int>(units), H, Nq, qtiles, q, ldq, k, v, ldkv, o, scale);
+  if (dh == 64) attention_nk32_f32_kernel<64><<<grid, 64, 0, s>>>(static_cast<int>(units), H, Nq, qtiles, q, ldq, k, v, ldkv, o, scale, round_tf32_out);
+  else attention_nk32_f32_kernel<32><<<grid, 64, 0, s>>>(static_cast<int>(units), H, Nq, qtiles, q, ldq, k, v, ldkv, o, scale, round_tf32_out);
   LDT_CUDA_OK(cudaGetLastError());
   return LDT_OK;
 }

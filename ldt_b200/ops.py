@@ -200,9 +200,10 @@ def pairwise_emd(a: torch.Tensor, b: torch.Tensor, row_begin: int = 0, row_end: 
 
 def gemm(A: torch.Tensor, W: torch.Tensor, bias, out: torch.Tensor, epilogue: int, *, N: int | None = None,
          K: int | None = None, resid=None, gate=None, gate_stride: int = 0, rows_per_gate: int = 1,
-         backend: int = 0) -> torch.Tensor:
+         backend: int = 0, split_operands: bool = False) -> torch.Tensor:
     """out = epilogue(A @ W[:N,:K].T + bias).  A bf16 [M, lda], W bf16 [>=N, ldw]; strides taken from tensors.
-    Both f32 (holding TF32-rounded values): the kind::tf32 contraction of the TF32 parity mode (operand_type 1)."""
+    Both f32 (holding TF32-rounded values): the kind::tf32 contraction of the TF32 parity mode (operand_type 1);
+    ``split_operands``: both laid out by :func:`split_tf32` (operand_type 2: the GELU epilogue then keeps full fp32)."""
     assert A.dtype == W.dtype and A.dtype in (torch.bfloat16, torch.float32) and A.dim() == 2 and W.dim() == 2
     assert A.stride(1) == 1 and W.stride(1) == 1 and out.stride(-1) == 1
     M = A.shape[0]
@@ -212,7 +213,7 @@ def gemm(A: torch.Tensor, W: torch.Tensor, bias, out: torch.Tensor, epilogue: in
     args = GemmArgs(M=M, N=N, K=K, A=ptr(A), lda=A.stride(0), W=ptr(W), ldw=W.stride(0), bias=ptr(bias),
                     out=ptr(out2), ldo=out2.stride(0), epilogue=epilogue, resid=ptr(resid), gate=ptr(gate),
                     gate_stride=gate_stride, rows_per_gate=rows_per_gate, backend=backend,
-                    operand_type=1 if A.dtype == torch.float32 else 0)
+                    operand_type=(2 if split_operands else 1) if A.dtype == torch.float32 else 0)
     with torch.cuda.device(A.device), _launch("gemm", 1, (M, N, K, epilogue)):
         check(load().ldt_gemm_bf16(C.byref(args), stream_ptr()), "ldt_gemm_bf16")
     return out
@@ -308,30 +309,36 @@ def round_pad_tf32(x: torch.Tensor, ld_out: int | None = None, out: torch.Tensor
     return out
 
 
-def split_tf32(x: torch.Tensor, ld_part: int | None = None, weight_side: bool = False) -> torch.Tensor:
+def split_tf32(x: torch.Tensor, ld_part: int | None = None, weight_side: bool = False, out: torch.Tensor | None = None,
+               silu: bool = False) -> torch.Tensor:
     """f32 [rows, cols] -> f32 [rows, 3*ld_part], the error-compensated TF32 operand layout ("3xTF32"): activations
-    [hi | hi | lo], weights [hi | lo | hi]; one kind::tf32 contraction over 3*ld_part then has fp32-grade accuracy."""
+    [hi | hi | lo], weights [hi | lo | hi]; one kind::tf32 contraction over 3*ld_part then has fp32-grade accuracy.
+    ``silu`` applies SiLU before the split (the adaLN input)."""
     _req(x, torch.float32, "x")
     rows, cols = x.shape
     ld_part = ((cols + 31) // 32) * 32 if ld_part is None else ld_part
-    out = torch.empty((rows, 3 * ld_part), dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty((rows, 3 * ld_part), dtype=torch.float32, device=x.device)
+    elif out.shape != (rows, 3 * ld_part) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise RuntimeError(f"split_tf32: out must be contiguous f32 {(rows, 3 * ld_part)}")
     with torch.cuda.device(x.device), _launch("split_tf32"):
-        check(load().ldt_split_tf32(rows, cols, ptr(x), x.stride(0), ptr(out), ld_part, int(weight_side), stream_ptr()), "ldt_split_tf32")
+        check(load().ldt_split_tf32(rows, cols, ptr(x), x.stride(0), ptr(out), ld_part, int(weight_side), int(silu), stream_ptr()),
+              "ldt_split_tf32")
     return out
 
 
 def layernorm_mod_f32(x: torch.Tensor, out: torch.Tensor, *, shift=None, scale=None, mod_stride: int = 0,
-                      rows_per_mod: int = 1, weight=None, bias=None, eps: float = 1e-6) -> torch.Tensor:
+                      rows_per_mod: int = 1, weight=None, bias=None, eps: float = 1e-6, round_tf32: bool = True) -> torch.Tensor:
     rows, Cc = x.shape
     with torch.cuda.device(x.device), _launch("layernorm"):
         check(load().ldt_layernorm_mod_f32(rows, Cc, ptr(x), ptr(shift), ptr(scale), mod_stride, rows_per_mod,
-                                           ptr(weight), ptr(bias), eps, ptr(out), stream_ptr()), "ldt_layernorm_mod_f32")
+                                           ptr(weight), ptr(bias), eps, ptr(out), int(round_tf32), stream_ptr()), "ldt_layernorm_mod_f32")
     return out
 
 
-def attention_nk32_f32(B: int, H: int, Nq: int, dh: int, q, ldq: int, k, v, ldkv: int, o) -> None:
+def attention_nk32_f32(B: int, H: int, Nq: int, dh: int, q, ldq: int, k, v, ldkv: int, o, round_tf32: bool = True) -> None:
     with torch.cuda.device(o.device), _launch("attention"):
-        check(load().ldt_attention_nk32_f32(B, H, Nq, dh, ptr(q), ldq, ptr(k), ptr(v), ldkv, ptr(o), stream_ptr()),
+        check(load().ldt_attention_nk32_f32(B, H, Nq, dh, ptr(q), ldq, ptr(k), ptr(v), ldkv, ptr(o), int(round_tf32), stream_ptr()),
               "ldt_attention_nk32_f32")
 
 

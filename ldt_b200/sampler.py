@@ -97,6 +97,9 @@ def modulation_table(score, P, timesteps: torch.Tensor, chunk: int = 256) -> tor
         if score.precision == "tf32":
             Q = score.packed_tf32()
             ops.gemm(ops.round_pad_tf32(c, silu=True), Q["w_ada"], Q["b_ada"], table[s:e], ops.EPI_BIAS_F32)
+        elif score.precision == "fp32":
+            Q = score.packed_tf32()
+            ops.gemm(ops.split_tf32(c, silu=True), Q["w_ada"], Q["b_ada"], table[s:e], ops.EPI_BIAS_F32, split_operands=True)
         else:
             ops.gemm(sc, P["w_ada"], P["b_ada"], table[s:e], ops.EPI_BIAS_F32)
     return table
@@ -263,8 +266,8 @@ def fused_sample_loop(score, sde, x0, N, predictor, time_eps, probability_flow, 
     device = x0.device
     B = x0.shape[0]
     per_sample_c, cross = extra is not None, cond_tokens is not None
-    if score.precision == "tf32" and (per_sample_c or cross):
-        raise NotImplementedError("precision='tf32' samples conditionally through the per-step path only")
+    if score.precision in ("tf32", "fp32") and (per_sample_c or cross):
+        raise NotImplementedError("precision='tf32' / 'fp32' sample conditionally through the per-step path only")
     key = (score.precision, B, N, predictor, float(time_eps), bool(probability_flow), device, use_graph,
            per_sample_c, cross, corrector_steps, float(snr), score._fingerprint())
     sg = _graph_cache.get(key)

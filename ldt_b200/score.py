@@ -186,7 +186,9 @@ class Score(nn.Module):
         # "bf16" (product path: bf16 operands, fp32 accumulate) or "tf32": the parity mode -- fp32 activations end to end
         # and kind::tf32 contractions, the precision of the reference's own GPU arithmetic (cuDNN TF32 convolutions).
         # ~4x tighter against the fp32 reference than bf16 (tests/test_gpu_model.py), about half the speed; plain (non-UNet)
-        # score nets with head dim 32 or 64.
+        # score nets with head dim 32 or 64.  "fp32": the same pipeline with every contraction operand split hi + lo (3xTF32,
+        # ldt_split_tf32) and no intermediate rounding: ~1e-5 against the fp32 reference (SURVEY 8(d)'s <= 1e-4 bar), ~6x the
+        # contraction work -- a parity instrument.
         self.precision = "bf16"
         # the token pass of the shipped configuration (plain AdaLN blocks, head dim 64, self-attention) goes through the
         # whole-path C entry point ldt_score_forward: one ctypes call instead of ~150 (same kernels, same order, same bits;
@@ -216,15 +218,19 @@ class Score(nn.Module):
         self._generation = getattr(self, "_generation", 0) + 1
 
     def packed_tf32(self):
-        """fp32 copies of the contraction weights rounded to TF32 (K padded to 32), for precision = "tf32"."""
-        key = self._fingerprint()
+        """fp32 copies of the contraction weights for the two f32-operand modes: rounded to TF32 (precision = "tf32") or in
+        the [hi | lo | hi] split layout of ldt_split_tf32 (precision = "fp32", 3xTF32); K padded to 32 per part."""
+        split = self.precision == "fp32"
+        key = (split,) + self._fingerprint()
         if getattr(self, "_packed32", None) is not None and key == self._packed32_key:
             return self._packed32
         if self.unet:
-            raise NotImplementedError("ldt_b200.Score: precision='tf32' covers the plain (non-UNet) score net")
+            raise NotImplementedError("ldt_b200.Score: precision='tf32' / 'fp32' cover the plain (non-UNet) score net")
 
-        def rw(w):   # [out, in, 1] or [out, in] parameter -> rounded f32 [out, pad32(in)]
+        def rw(w):   # [out, in, 1] or [out, in] parameter -> f32 [out, pad32(in)] rounded, or [out, 3*pad32(in)] split
             w2 = w.detach().reshape(w.shape[0], -1).float().contiguous()
+            if split:
+                return ops.split_tf32(w2, _pad_to(w2.shape[1], 32), weight_side=True)
             return ops.round_pad_tf32(w2, _pad_to(w2.shape[1], 32))
 
         def fb(b):
@@ -262,52 +268,72 @@ class Score(nn.Module):
                   "att": torch.empty((M, Hd), dtype=f32, device=device), "hid": torch.empty((M, 4 * Hd), dtype=f32, device=device),
                   "h": torch.empty((M, Hd), dtype=f32, device=device)}
             self._ws32[M] = ws
+        if self.precision == "fp32" and "a3" not in ws:   # [hi | hi | lo] operand buffers of the 3xTF32 mode
+            Hd, f32 = self.hidden_size, torch.float32
+            ws["xa3"] = torch.empty((M, 3 * _pad_to(self.z_dim, 32)), dtype=f32, device=device)
+            ws["a3"] = torch.empty((M, 3 * Hd), dtype=f32, device=device)
+            ws["hid3"] = torch.empty((M, 12 * Hd), dtype=f32, device=device)
         return ws
 
     def _run_tokens_tf32(self, x_tokens, mod, mod_stride, out, cond_tokens=None):
-        """run_tokens with fp32 activations and kind::tf32 contractions (precision = "tf32")."""
+        """run_tokens with fp32 activations and kind::tf32 contractions: precision = "tf32" (operands rounded to TF32 where
+        they are produced) or "fp32" (producers keep full fp32, every contraction operand is split hi + lo: 3xTF32)."""
         Q = self.packed_tf32()
+        split = self.precision == "fp32"
+        rnd = not split
         Hd, T = self.hidden_size, self.z_scale
         M = x_tokens.shape[0]
         B = M // T
         heads, dh = self.num_heads, Hd // self.num_heads
         if dh not in (32, 64):
-            raise NotImplementedError("ldt_b200.Score: precision='tf32' needs head dim 32 or 64")
+            raise NotImplementedError("ldt_b200.Score: precision='tf32' / 'fp32' need head dim 32 or 64")
         ws = self._workspace_tf32(M, x_tokens.device)
         mp = mod.data_ptr()
 
         def mview(off):
             return _PtrView(mp + 4 * off)
 
+        def gemm(act, buf3, W, b, o, epi, **kw):   # act: f32 activations [M, K]; buf3: its split buffer in the fp32 mode
+            if split:
+                return ops.gemm(ops.split_tf32(act, W.shape[1] // 3, out=buf3), W, b, o, epi, split_operands=True, **kw)
+            return ops.gemm(act, W, b, o, epi, **kw)
+
         h, a, qkv, att, hid = ws["h"], ws["a"], ws["qkv"], ws["att"], ws["hid"]
-        ops.round_pad_tf32(x_tokens, ws["xa"].shape[1], out=ws["xa"])
-        ops.gemm(ws["xa"], Q["w_in"], Q["b_in"], h, EPI_BIAS_F32)
+        a3, hid3 = ws.get("a3"), ws.get("hid3")
+        if split:
+            ops.gemm(ops.split_tf32(x_tokens, ws["xa3"].shape[1] // 3, out=ws["xa3"]), Q["w_in"], Q["b_in"], h, EPI_BIAS_F32,
+                     split_operands=True)
+        else:
+            ops.round_pad_tf32(x_tokens, ws["xa"].shape[1], out=ws["xa"])
+            ops.gemm(ws["xa"], Q["w_in"], Q["b_in"], h, EPI_BIAS_F32)
         kvc = None
-        if cond_tokens is not None:   # condition tokens [B, hidden, T] -> token-major, rounded: K/V source of the even blocks
-            kvc = ops.round_pad_tf32(cond_tokens.transpose(1, 2).contiguous().view(M, Hd).float())
+        if cond_tokens is not None:   # condition tokens [B, hidden, T] -> token-major: K/V source of the even blocks
+            kvc = cond_tokens.transpose(1, 2).contiguous().view(M, Hd).float()
+            kvc = ops.split_tf32(kvc, Hd) if split else ops.round_pad_tf32(kvc)
             kv = torch.empty((M, 2 * Hd), dtype=torch.float32, device=h.device)
         k = _PtrView(qkv.data_ptr() + 4 * Hd)
         v = _PtrView(qkv.data_ptr() + 8 * Hd)
         for i, W in enumerate(Q["blocks"]):
             base = i * 6 * Hd
-            ops.layernorm_mod_f32(h, a, shift=mview(base), scale=mview(base + Hd), mod_stride=mod_stride, rows_per_mod=T)
+            ops.layernorm_mod_f32(h, a, shift=mview(base), scale=mview(base + Hd), mod_stride=mod_stride, rows_per_mod=T,
+                                  round_tf32=rnd)
             if kvc is not None and i % 2 == 0:
-                ops.gemm(a, W["w_qkv"], W["b_qkv"], qkv, EPI_BIAS_F32, N=Hd)
-                ops.gemm(kvc, W["w_qkv"][Hd:], W["b_qkv"][Hd:], kv, EPI_BIAS_F32)
-                ops.attention_nk32_f32(B, heads, T, dh, qkv, 3 * Hd, kv, _PtrView(kv.data_ptr() + 4 * Hd), 2 * Hd, att)
+                gemm(a, a3, W["w_qkv"], W["b_qkv"], qkv, EPI_BIAS_F32, N=Hd)
+                ops.gemm(kvc, W["w_qkv"][Hd:], W["b_qkv"][Hd:], kv, EPI_BIAS_F32, split_operands=split)
+                ops.attention_nk32_f32(B, heads, T, dh, qkv, 3 * Hd, kv, _PtrView(kv.data_ptr() + 4 * Hd), 2 * Hd, att, round_tf32=rnd)
             else:
-                ops.gemm(a, W["w_qkv"], W["b_qkv"], qkv, EPI_BIAS_F32)
-                ops.attention_nk32_f32(B, heads, T, dh, qkv, 3 * Hd, k, v, 3 * Hd, att)
-            ops.gemm(att, W["w_o"], W["b_o"], h, EPI_GATE_RESID_F32, resid=h, gate=mview(base + 2 * Hd),
-                     gate_stride=mod_stride, rows_per_gate=T)
+                gemm(a, a3, W["w_qkv"], W["b_qkv"], qkv, EPI_BIAS_F32)
+                ops.attention_nk32_f32(B, heads, T, dh, qkv, 3 * Hd, k, v, 3 * Hd, att, round_tf32=rnd)
+            gemm(att, a3, W["w_o"], W["b_o"], h, EPI_GATE_RESID_F32, resid=h, gate=mview(base + 2 * Hd),
+                 gate_stride=mod_stride, rows_per_gate=T)
             ops.layernorm_mod_f32(h, a, shift=mview(base + 3 * Hd), scale=mview(base + 4 * Hd), mod_stride=mod_stride,
-                                  rows_per_mod=T)
-            ops.gemm(a, W["w_fc1"], W["b_fc1"], hid, EPI_BIAS_GELU_F32)
-            ops.gemm(hid, W["w_fc2"], W["b_fc2"], h, EPI_GATE_RESID_F32, resid=h, gate=mview(base + 5 * Hd),
-                     gate_stride=mod_stride, rows_per_gate=T)
+                                  rows_per_mod=T, round_tf32=rnd)
+            gemm(a, a3, W["w_fc1"], W["b_fc1"], hid, EPI_BIAS_GELU_F32)
+            gemm(hid, hid3, W["w_fc2"], W["b_fc2"], h, EPI_GATE_RESID_F32, resid=h, gate=mview(base + 5 * Hd),
+                 gate_stride=mod_stride, rows_per_gate=T)
         base = self.num_blocks * 6 * Hd
-        ops.layernorm_mod_f32(h, a, shift=mview(base), scale=mview(base + Hd), mod_stride=mod_stride, rows_per_mod=T)
-        ops.gemm(a, Q["w_out"], Q["b_out"], out, EPI_BIAS_F32, N=self.z_dim)
+        ops.layernorm_mod_f32(h, a, shift=mview(base), scale=mview(base + Hd), mod_stride=mod_stride, rows_per_mod=T, round_tf32=rnd)
+        gemm(a, a3, Q["w_out"], Q["b_out"], out, EPI_BIAS_F32, N=self.z_dim)
         return out
 
     def packed(self):
@@ -403,6 +429,10 @@ class Score(nn.Module):
             Q = self.packed_tf32()
             ops.gemm(ops.round_pad_tf32(ws.c, silu=True), Q["w_ada"], Q["b_ada"], ws.mod, EPI_BIAS_F32)
             return ws.mod
+        if self.precision == "fp32":
+            Q = self.packed_tf32()
+            ops.gemm(ops.split_tf32(ws.c, silu=True), Q["w_ada"], Q["b_ada"], ws.mod, EPI_BIAS_F32, split_operands=True)
+            return ws.mod
         ops.gemm(ws.sc, P["w_ada"], P["b_ada"], ws.mod, EPI_BIAS_F32)
         return ws.mod
 
@@ -446,9 +476,9 @@ class Score(nn.Module):
     def run_tokens(self, P, ws, x_tokens, mod, mod_stride, out, kv_cond=None):
         """The per-step token path: x_tokens f32 [M, z_dim] -> out f32 [M, z_dim].  ``mod`` holds the AdaLN
         rows (one row broadcast when mod_stride == 0, else one per sample)."""
-        if self.precision not in ("bf16", "tf32"):
-            raise ValueError(f"ldt_b200.Score.precision must be 'bf16' or 'tf32', got {self.precision!r}")
-        if self.precision == "tf32":
+        if self.precision not in ("bf16", "tf32", "fp32"):
+            raise ValueError(f"ldt_b200.Score.precision must be 'bf16', 'tf32' or 'fp32', got {self.precision!r}")
+        if self.precision in ("tf32", "fp32"):
             return self._run_tokens_tf32(x_tokens, mod, mod_stride, out, cond_tokens=getattr(self, "_cond_tokens32", None))
         if self.unet:
             return self._run_tokens_unet(P, ws, x_tokens, mod, mod_stride, out, kv_cond)
@@ -591,7 +621,7 @@ class Score(nn.Module):
             if label is None and torch.is_tensor(cond_vec):
                 extra = cond_vec.float().expand(B, self.t_dim).contiguous()  # c = t_emb + condition[1]  (score.py:135)
             if torch.is_tensor(cond_tokens):
-                if self.precision == "tf32":
+                if self.precision in ("tf32", "fp32"):
                     self._cond_tokens32 = cond_tokens
                 else:
                     kv_cond = self.project_condition_tokens(P, cond_tokens)

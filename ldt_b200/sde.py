@@ -232,7 +232,7 @@ class DiffusionVPSDE:
             fusable = (predictor is not None and (corrector is None or corrector == "ancestral")
                        and not isinstance(condition, dict))
             owner_model = getattr(getattr(score_fn, "__self__", None), "model", None)
-            if getattr(owner_model, "precision", "bf16") == "tf32" and (condition is not None or label is not None):
+            if getattr(owner_model, "precision", "bf16") in ("tf32", "fp32") and (condition is not None or label is not None):
                 fusable = False   # the TF32 parity mode samples conditionally through the per-step path
             score_mod = None
             if fusable:   # one real call of score_fn must reproduce what the fused step hard-wires (sampler.py)

@@ -64,7 +64,7 @@ def test_argument_validation_without_gpu():
     assert b"ld_out" in L.ldt_last_error_string()
     assert L.ldt_group_features(0, 64, 4, 8, 16, None, None, None, None, 0, None, None, None, None, 64, None) == 0
     assert L.ldt_group_max(0, 8, 16, None, 16, None, 16, None) == 0 and L.ldt_group_max(4, 0, 16, None, 16, None, 16, None) == -1
-    assert L.ldt_split_tf32(4, 40, None, 40, None, 32, 0, None) == -1 and b"ld_part" in L.ldt_last_error_string()
+    assert L.ldt_split_tf32(4, 40, None, 40, None, 32, 0, 0, None) == -1 and b"ld_part" in L.ldt_last_error_string()
     a = _lib.GemmArgs(M=128, N=128, K=96, operand_type=1, epilogue=1)
     a.lda = a.ldw = 96
     a.ldo = 128
