@@ -170,6 +170,8 @@ class Compressor(nn.Module):
         self.reset_parameters()
         self._packed = None
         self._packed_key = None
+        # "bf16": the product decoder (bf16 operands, fp32 accumulate); "fp32": the 3xTF32 parity mode of sample() (_decode_fp32)
+        self.precision = "bf16"
 
     def reset_parameters(self):
         """torch's per-layer default initialisers drawn in the reference's CONSTRUCTION order (Network.py:125-157: input,
@@ -237,6 +239,7 @@ class Compressor(nn.Module):
         self._packed = None
         self._packed_key = None
         self._packed_pro = None
+        self._packed_f32 = None
         self._generation = getattr(self, "_generation", 0) + 1
 
     def packed(self):
@@ -344,6 +347,11 @@ class Compressor(nn.Module):
             hid = torch.empty((MQ, int(self.mlp_ratio * H)), dtype=bf, device=dev)
             bufs = (e_a, xx, kv, a, q, att, hid)
             pts8 = torch.empty((MQ, 8), dtype=torch.float32, device=dev)
+            if getattr(self, "precision", "bf16") == "fp32":
+                out = self._decode_fp32(B, num_points, eps, o)
+                return self.postprocess(out)
+            if getattr(self, "precision", "bf16") != "bf16":
+                raise ValueError(f"ldt_b200.Compressor.precision must be 'bf16' or 'fp32', got {self.precision!r}")
             if getattr(self, "c_path", True):
                 # the whole decoder as ONE call of the C entry point ldt_decoder_forward (same kernels, same order, same bits)
                 from . import _lib
@@ -369,6 +377,50 @@ class Compressor(nn.Module):
                 ops.gemm(ob, P["w_out"], P["b_out"], pts8, EPI_BIAS_F32)               # self.output(o)           :266
             out = pts8[:, :3].reshape(B, num_points, 3).contiguous()
         return self.postprocess(out)
+
+    def _decode_fp32(self, B, num_points, eps, o):
+        """The decoder in the fp32 parity mode (``precision = "fp32"``): the same layer sequence with fp32 activations, 3xTF32
+        contractions (grouping.conv_rows), fp32 LayerNorm / attention / GELU without intermediate rounding.  A parity
+        instrument like Score.precision = "fp32" (DESIGN.md 4.8); eps f32 [B*32, n_layers*z_dim], o f32 [B*N, H] in place."""
+        from . import grouping
+        from ._lib import EPI_BIAS_GELU_F32
+        H, T, Z, heads = self.hidden_dim, self.z_scales, self.z_dim, self.num_heads
+        key = self._fingerprint()
+        if getattr(self, "_packed_f32", None) is None or self._packed_f32_key != key:
+            Q = []
+            for l in range(self.n_layers):
+                d = self.decoder._modules[str(l)]
+                a = d.att1
+                Q.append({"ln": grouping.pack_tf32(d.ln), "kv": grouping.pack_tf32(a.fc_kv), "q": grouping.pack_tf32(a.fc_q),
+                          "o": grouping.pack_tf32(a.fc_o), "fc1": grouping.pack_tf32(a.mlp.fc._modules["0"]._modules["0"]),
+                          "fc2": grouping.pack_tf32(a.mlp.out),
+                          "n1w": a.norm1.norm.weight.detach().float().contiguous(), "n1b": a.norm1.norm.bias.detach().float().contiguous(),
+                          "n2w": a.norm2.norm.weight.detach().float().contiguous(), "n2b": a.norm2.norm.bias.detach().float().contiguous()})
+            w_out = torch.zeros((8, H), dtype=torch.float32, device=o.device)   # N padded to 8 rows (the GEMM core's N % 8 rule)
+            w_out[:3] = self.output.weight.detach().reshape(3, H)
+            b_out = torch.zeros(8, dtype=torch.float32, device=o.device)
+            b_out[:3] = self.output.bias.detach()
+            self._packed_f32 = {"layers": Q, "out": (ops.split_tf32(w_out, H, weight_side=True), b_out)}
+            self._packed_f32_key = key
+        Q = self._packed_f32
+        MQ = B * num_points
+        a = torch.empty((MQ, H), dtype=torch.float32, device=o.device)
+        att = torch.empty((MQ, H), dtype=torch.float32, device=o.device)
+        for idx in range(self.n_layers):
+            W = Q["layers"][self.n_layers - 1 - idx]                                   # reversed(self.decoder)   :263
+            chunk = eps[:, idx * Z:(idx + 1) * Z].contiguous()                         # torch.split(...)[idx]    :262
+            xx = grouping.conv_rows(chunk, W["ln"])                                    # x = self.ln(eps)          :81
+            kv = grouping.conv_rows(xx, W["kv"])                                       # fc_kv(x): raw, un-normalised x
+            ops.layernorm_mod_f32(o, a, weight=W["n1w"], bias=W["n1b"], round_tf32=False)
+            q = grouping.conv_rows(a, W["q"])
+            ops.attention_nk32_f32(B, heads, num_points, H // heads, q, H, kv, _PtrView(kv.data_ptr() + 4 * H), 2 * H, att,
+                                   round_tf32=False)
+            grouping.conv_rows(att, W["o"], EPI_GATE_RESID_F32, resid=o, out=o)         # o = o + fc_o(att)
+            ops.layernorm_mod_f32(o, a, weight=W["n2w"], bias=W["n2b"], round_tf32=False)
+            hid = grouping.conv_rows(a, W["fc1"], EPI_BIAS_GELU_F32)
+            grouping.conv_rows(hid, W["fc2"], EPI_GATE_RESID_F32, resid=o, out=o)
+        pts8 = grouping.conv_rows(o, Q["out"])                                         # self.output(o)            :266
+        return pts8[:, :3].reshape(B, num_points, 3).contiguous()
 
     def _decoder_block(self, W, B, num_points, chunk, ld_chunk, o, bufs):
         """DecoderBlock.forward (:80-83): o [B*N, H] f32 (in place) attends to the layer's latent chunk [B*32, z_dim]."""

@@ -40,13 +40,13 @@ def pack_tf32(conv, bn=None):
     return ops.split_tf32(W, _pad32(W.shape[1]), weight_side=True), b
 
 
-def conv_rows(x: torch.Tensor, packed, epilogue: int = EPI_BIAS_F32, resid=None) -> torch.Tensor:
-    """rows [M, >= in] f32 -> [M, out] f32: split into [hi | hi | lo], then one kind::tf32 contraction over 3*pad32(in)."""
+def conv_rows(x: torch.Tensor, packed, epilogue: int = EPI_BIAS_F32, resid=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """rows [M, <= pad32(in)] f32 -> [M, out] f32: split into [hi | hi | lo], then one kind::tf32 contraction over 3*pad32(in)."""
     W, b = packed
-    ld_part = W.shape[1] // 3
-    x3 = ops.split_tf32(x if x.shape[1] <= ld_part else x[:, :ld_part], ld_part)
-    out = torch.empty((x.shape[0], W.shape[0]), dtype=torch.float32, device=x.device)
-    return ops.gemm(x3, W, b, out, epilogue, resid=resid)
+    x3 = ops.split_tf32(x, W.shape[1] // 3)
+    if out is None:
+        out = torch.empty((x.shape[0], W.shape[0]), dtype=torch.float32, device=x.device)
+    return ops.gemm(x3, W, b, out, epilogue, resid=resid, split_operands=True)
 
 
 def pack_grouper(g) -> dict:
