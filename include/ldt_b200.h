@@ -232,6 +232,9 @@ int ldt_layernorm_mod_f32(int rows, int C, const float* x, const float* shift, c
                           void* stream);
 int ldt_attention_nk32_f32(int B, int H, int Nq, int dh, const float* q, int ldq, const float* k, const float* v, int ldkv,
                            float* o, int round_tf32_out, void* stream);
+/* ldt_attention_longkv on f32 q / k / v with an f32 output (the fp32 parity mode of Compressor.forward's posterior blocks). */
+int ldt_attention_longkv_f32(int B, int H, int Nq, int Nk, int dh, const float* q, int ldq, const float* k, const float* v,
+                             int ldkv, float* o, void* stream);
 
 /* Multi-head attention over a short key set, one (batch, head) pair per warp group.
  *   q  bf16 [B*Nq, ldq]  (head h uses columns h*dh..h*dh+dh-1 -- contiguous channel groups,

@@ -378,47 +378,101 @@ class Compressor(nn.Module):
             out = pts8[:, :3].reshape(B, num_points, 3).contiguous()
         return self.postprocess(out)
 
+    def _packed_fp32(self):
+        """3xTF32 ([hi | lo | hi]) copies of every contraction weight of the decoder, the posterior blocks and the encoder:
+        the fp32 parity mode (``precision = "fp32"``) of sample() and forward()."""
+        from . import grouping
+        key = self._fingerprint()
+        if getattr(self, "_packed_f32", None) is not None and self._packed_f32_key == key:
+            return self._packed_f32
+        f32 = lambda t: t.detach().float().contiguous()
+        H = self.hidden_dim
+
+        def block(a, affine):
+            W = {"kv": grouping.pack_tf32(a.fc_kv), "q": grouping.pack_tf32(a.fc_q), "o": grouping.pack_tf32(a.fc_o),
+                 "fc1": grouping.pack_tf32(a.mlp.fc._modules["0"]._modules["0"]), "fc2": grouping.pack_tf32(a.mlp.out)}
+            if affine:
+                W.update(n1w=f32(a.norm1.norm.weight), n1b=f32(a.norm1.norm.bias), n2w=f32(a.norm2.norm.weight), n2b=f32(a.norm2.norm.bias))
+            return W
+
+        with torch.no_grad():
+            Q = {"layers": [], "post": [], "enc": []}
+            ada_w, ada_b = [], []
+            for l in range(self.n_layers):
+                d = self.decoder._modules[str(l)]
+                Q["layers"].append({"ln": grouping.pack_tf32(d.ln), **block(d.att1, True)})
+                Q["post"].append({**block(d.att, True), "prior": grouping.pack_tf32(d.prior._modules["1"])})
+                e = self.encoder._modules[str(l)]
+                blocks = []
+                for j in range(self.cfg.encoder_layers):
+                    a = e.atts._modules[str(j)]
+                    blocks.append(block(a, False))
+                    ada_w.append(a.adaLN._modules["1"].weight.detach())
+                    ada_b.append(a.adaLN._modules["1"].bias.detach())
+                ada_w.append(e.conv_out.adaLN._modules["1"].weight.detach())
+                ada_b.append(e.conv_out.adaLN._modules["1"].bias.detach())
+                Q["enc"].append({"blocks": blocks, "out": grouping.pack_tf32(e.conv_out.ln)})
+            wa = torch.cat(ada_w, dim=0).float().contiguous()
+            Q["ada"] = (ops.split_tf32(wa, _pad_to(wa.shape[1], 32), weight_side=True), torch.cat(ada_b).float().contiguous())
+            w_out = torch.zeros((8, H), dtype=torch.float32, device=wa.device)     # N padded to 8 rows (the GEMM core's N % 8 rule)
+            w_out[:3] = self.output.weight.detach().reshape(3, H)
+            b_out = torch.zeros(8, dtype=torch.float32, device=wa.device)
+            b_out[:3] = self.output.bias.detach()
+            Q["out"] = (ops.split_tf32(w_out, H, weight_side=True), b_out)
+        self._packed_f32, self._packed_f32_key = Q, key
+        return Q
+
+    def _attn_block_fp32(self, W, B, x, kv_src, kv_tokens, n1, n2, gate1, gate2, mod_stride=0):
+        """_attn_block in the fp32 parity mode: x f32 [B*32, H] in place, kv_src f32 [B*kv_tokens, H] (raw, un-normalised)."""
+        from . import grouping
+        from ._lib import EPI_BIAS_GELU_F32
+        H, T, heads = self.hidden_dim, self.z_scales, self.num_heads
+        a = torch.empty_like(x)
+        att = torch.empty_like(x)
+        ops.layernorm_mod_f32(x, a, round_tf32=False, **n1)
+        q = grouping.conv_rows(a, W["q"])
+        kv = grouping.conv_rows(kv_src, W["kv"])
+        vptr = _PtrView(kv.data_ptr() + 4 * H)
+        if kv_tokens == 32:
+            ops.attention_nk32_f32(B, heads, T, H // heads, q, H, kv, vptr, 2 * H, att, round_tf32=False)
+        else:
+            ops.attention_longkv_f32(B, heads, T, kv_tokens, H // heads, q, H, kv, vptr, 2 * H, att)
+        ops.gemm(ops.split_tf32(att, H), W["o"][0], W["o"][1], x, EPI_GATE_RESID_F32, resid=x, gate=gate1, gate_stride=mod_stride,
+                 rows_per_gate=T, split_operands=True)
+        ops.layernorm_mod_f32(x, a, round_tf32=False, **n2)
+        hid = grouping.conv_rows(a, W["fc1"], EPI_BIAS_GELU_F32)
+        ops.gemm(ops.split_tf32(hid, hid.shape[1]), W["fc2"][0], W["fc2"][1], x, EPI_GATE_RESID_F32, resid=x, gate=gate2,
+                 gate_stride=mod_stride, rows_per_gate=T, split_operands=True)
+
+    def _decoder_block_fp32(self, W, B, num_points, chunk, o):
+        """DecoderBlock.forward (:80-83) in the fp32 parity mode: o f32 [B*N, H] (in place) attends to chunk f32 [B*32, z_dim]."""
+        from . import grouping
+        from ._lib import EPI_BIAS_GELU_F32
+        H, heads = self.hidden_dim, self.num_heads
+        a = torch.empty_like(o)
+        att = torch.empty_like(o)
+        xx = grouping.conv_rows(chunk, W["ln"])                                        # x = self.ln(eps)          :81
+        kv = grouping.conv_rows(xx, W["kv"])                                           # fc_kv(x): raw, un-normalised x
+        ops.layernorm_mod_f32(o, a, weight=W["n1w"], bias=W["n1b"], round_tf32=False)
+        q = grouping.conv_rows(a, W["q"])
+        ops.attention_nk32_f32(B, heads, num_points, H // heads, q, H, kv, _PtrView(kv.data_ptr() + 4 * H), 2 * H, att,
+                               round_tf32=False)
+        grouping.conv_rows(att, W["o"], EPI_GATE_RESID_F32, resid=o, out=o)             # o = o + fc_o(att)
+        ops.layernorm_mod_f32(o, a, weight=W["n2w"], bias=W["n2b"], round_tf32=False)
+        hid = grouping.conv_rows(a, W["fc1"], EPI_BIAS_GELU_F32)
+        grouping.conv_rows(hid, W["fc2"], EPI_GATE_RESID_F32, resid=o, out=o)
+
     def _decode_fp32(self, B, num_points, eps, o):
         """The decoder in the fp32 parity mode (``precision = "fp32"``): the same layer sequence with fp32 activations, 3xTF32
         contractions (grouping.conv_rows), fp32 LayerNorm / attention / GELU without intermediate rounding.  A parity
         instrument like Score.precision = "fp32" (DESIGN.md 4.8); eps f32 [B*32, n_layers*z_dim], o f32 [B*N, H] in place."""
         from . import grouping
-        from ._lib import EPI_BIAS_GELU_F32
-        H, T, Z, heads = self.hidden_dim, self.z_scales, self.z_dim, self.num_heads
-        key = self._fingerprint()
-        if getattr(self, "_packed_f32", None) is None or self._packed_f32_key != key:
-            Q = []
-            for l in range(self.n_layers):
-                d = self.decoder._modules[str(l)]
-                a = d.att1
-                Q.append({"ln": grouping.pack_tf32(d.ln), "kv": grouping.pack_tf32(a.fc_kv), "q": grouping.pack_tf32(a.fc_q),
-                          "o": grouping.pack_tf32(a.fc_o), "fc1": grouping.pack_tf32(a.mlp.fc._modules["0"]._modules["0"]),
-                          "fc2": grouping.pack_tf32(a.mlp.out),
-                          "n1w": a.norm1.norm.weight.detach().float().contiguous(), "n1b": a.norm1.norm.bias.detach().float().contiguous(),
-                          "n2w": a.norm2.norm.weight.detach().float().contiguous(), "n2b": a.norm2.norm.bias.detach().float().contiguous()})
-            w_out = torch.zeros((8, H), dtype=torch.float32, device=o.device)   # N padded to 8 rows (the GEMM core's N % 8 rule)
-            w_out[:3] = self.output.weight.detach().reshape(3, H)
-            b_out = torch.zeros(8, dtype=torch.float32, device=o.device)
-            b_out[:3] = self.output.bias.detach()
-            self._packed_f32 = {"layers": Q, "out": (ops.split_tf32(w_out, H, weight_side=True), b_out)}
-            self._packed_f32_key = key
-        Q = self._packed_f32
-        MQ = B * num_points
-        a = torch.empty((MQ, H), dtype=torch.float32, device=o.device)
-        att = torch.empty((MQ, H), dtype=torch.float32, device=o.device)
+        Z = self.z_dim
+        Q = self._packed_fp32()
         for idx in range(self.n_layers):
             W = Q["layers"][self.n_layers - 1 - idx]                                   # reversed(self.decoder)   :263
             chunk = eps[:, idx * Z:(idx + 1) * Z].contiguous()                         # torch.split(...)[idx]    :262
-            xx = grouping.conv_rows(chunk, W["ln"])                                    # x = self.ln(eps)          :81
-            kv = grouping.conv_rows(xx, W["kv"])                                       # fc_kv(x): raw, un-normalised x
-            ops.layernorm_mod_f32(o, a, weight=W["n1w"], bias=W["n1b"], round_tf32=False)
-            q = grouping.conv_rows(a, W["q"])
-            ops.attention_nk32_f32(B, heads, num_points, H // heads, q, H, kv, _PtrView(kv.data_ptr() + 4 * H), 2 * H, att,
-                                   round_tf32=False)
-            grouping.conv_rows(att, W["o"], EPI_GATE_RESID_F32, resid=o, out=o)         # o = o + fc_o(att)
-            ops.layernorm_mod_f32(o, a, weight=W["n2w"], bias=W["n2b"], round_tf32=False)
-            hid = grouping.conv_rows(a, W["fc1"], EPI_BIAS_GELU_F32)
-            grouping.conv_rows(hid, W["fc2"], EPI_GATE_RESID_F32, resid=o, out=o)
+            self._decoder_block_fp32(W, B, num_points, chunk, o)
         pts8 = grouping.conv_rows(o, Q["out"])                                         # self.output(o)            :266
         return pts8[:, :3].reshape(B, num_points, 3).contiguous()
 
@@ -515,6 +569,8 @@ class Compressor(nn.Module):
         x, pos = self.encoder_prologue(pts)
         B = x.shape[0]
         x = x.reshape(B * T, H).contiguous()                               # token-major residual stream
+        if getattr(self, "precision", "bf16") == "fp32":
+            return self._bottom_up_fp32(B, x, pos)
         # all adaLN rows of the encoder from SiLU(pos) in one GEMM
         sc = torch.empty((B, Pd), dtype=torch.bfloat16, device=dev)
         ops.cond_silu(torch.zeros((1, Pd), device=dev), None, pos, None, sc)
@@ -543,9 +599,74 @@ class Compressor(nn.Module):
             outputs.append(o)
         return {"outputs": outputs, "max": x.max()}
 
+    def _bottom_up_fp32(self, B, x, pos):
+        """The encoder blocks of bottom_up in the fp32 parity mode (same sequence, 3xTF32 contractions)."""
+        from . import grouping
+        cfg = self.cfg
+        Q = self._packed_fp32()
+        H, T = self.hidden_dim, self.z_scales
+        L = cfg.encoder_layers
+        row = (6 * L + 2) * H
+        mod = torch.empty((B, self.n_layers * row), dtype=torch.float32, device=x.device)
+        ops.gemm(ops.split_tf32(pos.contiguous(), silu=True), Q["ada"][0], Q["ada"][1], mod, EPI_BIAS_F32, split_operands=True)
+        stride = mod.shape[1]
+        mv = lambda off: _PtrView(mod.data_ptr() + 4 * off)
+        a = torch.empty_like(x)
+        outputs = []
+        for l in range(self.n_layers):
+            for j, W in enumerate(Q["enc"][l]["blocks"]):
+                base = l * row + j * 6 * H
+                self._attn_block_fp32(W, B, x, x.clone(), 32,                  # layer(x, x, pos): K/V from the raw x
+                                      dict(shift=mv(base), scale=mv(base + H), mod_stride=stride, rows_per_mod=T),
+                                      dict(shift=mv(base + 3 * H), scale=mv(base + 4 * H), mod_stride=stride, rows_per_mod=T),
+                                      mv(base + 2 * H), mv(base + 5 * H), mod_stride=stride)
+            base = l * row + L * 6 * H
+            ops.layernorm_mod_f32(x, a, shift=mv(base), scale=mv(base + H), mod_stride=stride, rows_per_mod=T, round_tf32=False)
+            outputs.append(grouping.conv_rows(a, Q["enc"][l]["out"]))
+        return {"outputs": outputs, "max": x.max()}
+
+    def _top_down_fp32(self, encoder_out, N):
+        """top_down in the fp32 parity mode; same generator consumption and returned dictionary as the bf16 path."""
+        from . import grouping
+        Q = self._packed_fp32()
+        H, T, Z = self.hidden_dim, self.z_scales, self.z_dim
+        B = encoder_out[0].shape[0] // T
+        o = self.initial_set(B, N)
+        MT = B * T
+        cf = lambda t, c: t.view(B, T, c).transpose(1, 2)
+        posteriors = [(o.view(B, N, H).transpose(1, 2).clone(), None, None)]
+        kls, all_eps, all_logqz = [], [], []
+        for idx in range(self.n_layers):
+            Li = self.n_layers - 1 - idx
+            W = Q["post"][Li]
+            x = encoder_out[Li].clone()
+            n1, n2 = dict(weight=W["n1w"], bias=W["n1b"]), dict(weight=W["n2w"], bias=W["n2b"])
+            if idx != 0:
+                self._attn_block_fp32(W, B, x, o, N, n1, n2, None, None)
+            else:
+                self._attn_block_fp32(W, B, x, x.clone(), 32, n1, n2, None, None)
+            post = torch.empty((MT, 2 * Z), dtype=torch.float32, device=x.device)
+            ops.gemm(ops.split_tf32(x, H, silu=True), W["prior"][0], W["prior"][1], post, EPI_BIAS_F32, split_operands=True)
+            mu = cf(post[:, :Z], Z)
+            logvar = cf(post[:, Z:], Z).clamp(self.cfg.min_sigma, 10.0)
+            noise = torch.randn(mu.shape).to(mu)
+            eps = mu + torch.exp(logvar / 2.0) * noise
+            logqz = -0.5 * torch.square(eps - mu) / torch.exp(logvar) - 0.5 * logvar - 0.9189385332
+            logpz = -0.5 * torch.square(eps) - 0.9189385332
+            self._decoder_block_fp32(Q["layers"][Li], B, N, eps.transpose(1, 2).reshape(MT, Z).contiguous(), o)
+            all_eps.append(eps)
+            posteriors.append((eps, mu, logvar))
+            kls.append(logqz - logpz)
+            all_logqz.append(logqz)
+        pts8 = grouping.conv_rows(o, Q["out"])
+        return {"set": pts8[:, :3].reshape(B, N, 3).contiguous(), "posteriors": posteriors, "kls": kls,
+                "all_logqz": all_logqz, "all_eps": all_eps}
+
     def top_down(self, encoder_out, num_points=None, label=None):
         """Stochastic top-down pass (Network.py:211-233).  Tensors in the returned dict use the reference's
         channels-first shapes ([B, z_dim, 32] latents, [B, N, 3] set)."""
+        if getattr(self, "precision", "bf16") == "fp32":
+            return self._top_down_fp32(encoder_out, num_points if num_points is not None else self.outsize)
         P = self.packed()
         dev = self.output.weight.device
         H, T, Z, heads = self.hidden_dim, self.z_scales, self.z_dim, self.num_heads

@@ -171,11 +171,17 @@ attention_nk32_kernel(int units, int H, int Nq, int qtiles, const __nv_bfloat16*
 // ------------------------------------------------------------------------------------------------
 constexpr int ATTL_WARPS = 8;   // queries per CTA
 
-template <int DH>
+__device__ __forceinline__ float attl_load(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float attl_load(const float* p) { return *p; }
+__device__ __forceinline__ void attl_store(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void attl_store(float* p, float v) { *p = v; }
+
+// T = __nv_bfloat16 (product path) or float (the fp32 parity mode of Compressor.forward: same kernel, plain fp32 in and out)
+template <int DH, typename T>
 __global__ void __launch_bounds__(ATTL_WARPS * 32)
-attention_longkv_kernel(int H, int Nq, int Nk, const __nv_bfloat16* __restrict__ q, int ldq,
-                        const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v, int ldkv,
-                        __nv_bfloat16* __restrict__ o, float scale_log2e) {
+attention_longkv_kernel(int H, int Nq, int Nk, const T* __restrict__ q, int ldq,
+                        const T* __restrict__ k, const T* __restrict__ v, int ldkv,
+                        T* __restrict__ o, float scale_log2e) {
   static_assert(DH == 32 || DH == 64, "lane d owns output channels d, d + 32, ...");
   constexpr int CPL = DH / 32;   // output channels per lane
   __shared__ float Ks[32][DH + 1], Vs[32][DH + 1], Qs[ATTL_WARPS][DH];
@@ -189,7 +195,7 @@ attention_longkv_kernel(int H, int Nq, int Nk, const __nv_bfloat16* __restrict__
   if (live) {
 #pragma unroll
     for (int c = 0; c < CPL; ++c)
-      Qs[warp][lane + 32 * c] = __bfloat162float(q[(static_cast<size_t>(b) * Nq + qi) * ldq + h * DH + lane + 32 * c]);
+      Qs[warp][lane + 32 * c] = attl_load(q + (static_cast<size_t>(b) * Nq + qi) * ldq + h * DH + lane + 32 * c);
   }
   float m = -INFINITY, l = 0.f, acc[CPL];
 #pragma unroll
@@ -200,8 +206,8 @@ attention_longkv_kernel(int H, int Nq, int Nk, const __nv_bfloat16* __restrict__
       const int key = i / DH, d = i % DH;
       const bool ok = k0 + key < Nk;
       const size_t off = (static_cast<size_t>(b) * Nk + k0 + key) * ldkv + h * DH + d;
-      Ks[key][d] = ok ? __bfloat162float(k[off]) : 0.f;
-      Vs[key][d] = ok ? __bfloat162float(v[off]) : 0.f;
+      Ks[key][d] = ok ? attl_load(k + off) : 0.f;
+      Vs[key][d] = ok ? attl_load(v + off) : 0.f;
     }
     __syncthreads();
     if (live) {
@@ -230,7 +236,7 @@ attention_longkv_kernel(int H, int Nq, int Nk, const __nv_bfloat16* __restrict__
   if (live) {
 #pragma unroll
     for (int c = 0; c < CPL; ++c)
-      o[((static_cast<size_t>(b) * H + h) * Nq + qi) * DH + lane + 32 * c] = __float2bfloat16_rn(acc[c] / l);
+      attl_store(o + ((static_cast<size_t>(b) * H + h) * Nq + qi) * DH + lane + 32 * c, acc[c] / l);
   }
 }
 
@@ -372,13 +378,31 @@ extern "C" int ldt_attention_longkv(int B, int H, int Nq, int Nk, int dh, const 
   LDT_REQUIRE(blocks < (1LL << 31), LDT_ERR_INVALID, "ldt_attention_longkv: too many work units");
   const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(dh));
   if (dh == 32)
-    attention_longkv_kernel<32><<<static_cast<int>(blocks), ATTL_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+    attention_longkv_kernel<32, __nv_bfloat16><<<static_cast<int>(blocks), ATTL_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
         H, Nq, Nk, static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k),
         static_cast<const __nv_bfloat16*>(v), ldkv, static_cast<__nv_bfloat16*>(o), scale_log2e);
   else
-    attention_longkv_kernel<64><<<static_cast<int>(blocks), ATTL_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+    attention_longkv_kernel<64, __nv_bfloat16><<<static_cast<int>(blocks), ATTL_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
         H, Nq, Nk, static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k),
         static_cast<const __nv_bfloat16*>(v), ldkv, static_cast<__nv_bfloat16*>(o), scale_log2e);
+  LDT_CUDA_OK(cudaGetLastError());
+  return LDT_OK;
+}
+
+extern "C" int ldt_attention_longkv_f32(int B, int H, int Nq, int Nk, int dh, const float* q, int ldq, const float* k, const float* v,
+                                        int ldkv, float* o, void* stream) {
+  LDT_REQUIRE(B >= 0 && H > 0 && Nq > 0 && Nk > 0, LDT_ERR_INVALID, "ldt_attention_longkv_f32: bad shape B=%d H=%d Nq=%d Nk=%d", B, H,
+              Nq, Nk);
+  LDT_REQUIRE(dh == 32 || dh == 64, LDT_ERR_UNSUPPORTED, "ldt_attention_longkv_f32: head dim %d not in {32,64}", dh);
+  if (B == 0) return LDT_OK;
+  LDT_REQUIRE(q && k && v && o, LDT_ERR_INVALID, "ldt_attention_longkv_f32: null pointer");
+  LDT_REQUIRE(ldq >= H * dh && ldkv >= H * dh, LDT_ERR_INVALID, "ldt_attention_longkv_f32: ldq=%d ldkv=%d must be >= H*dh", ldq, ldkv);
+  const long long blocks = static_cast<long long>(B) * H * ((Nq + ATTL_WARPS - 1) / ATTL_WARPS);
+  LDT_REQUIRE(blocks < (1LL << 31), LDT_ERR_INVALID, "ldt_attention_longkv_f32: too many work units");
+  const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(dh));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dh == 32) attention_longkv_kernel<32, float><<<static_cast<int>(blocks), ATTL_WARPS * 32, 0, st>>>(H, Nq, Nk, q, ldq, k, v, ldkv, o, scale_log2e);
+  else attention_longkv_kernel<64, float><<<static_cast<int>(blocks), ATTL_WARPS * 32, 0, st>>>(H, Nq, Nk, q, ldq, k, v, ldkv, o, scale_log2e);
   LDT_CUDA_OK(cudaGetLastError());
   return LDT_OK;
 }

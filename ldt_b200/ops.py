@@ -342,6 +342,12 @@ def attention_nk32_f32(B: int, H: int, Nq: int, dh: int, q, ldq: int, k, v, ldkv
               "ldt_attention_nk32_f32")
 
 
+def attention_longkv_f32(B: int, H: int, Nq: int, Nk: int, dh: int, q, ldq: int, k, v, ldkv: int, o) -> None:
+    with torch.cuda.device(o.device), _launch("attention"):
+        check(load().ldt_attention_longkv_f32(B, H, Nq, Nk, dh, ptr(q), ldq, ptr(k), ptr(v), ldkv, ptr(o), stream_ptr()),
+              "ldt_attention_longkv_f32")
+
+
 def score_forward(plan, launches: int, x_tokens, mod, mod_stride: int, out) -> None:
     """The whole token pass as one C call (ldt_score_forward); ``plan`` is a _lib.ScorePlan, ``launches`` its kernel count."""
     with torch.cuda.device(out.device), _launch("score_forward", launches):

@@ -914,6 +914,36 @@ def test_compressor_forward_vs_reference_golden(dev):
     assert rms_rel_err(out["all_eps"], emu["all_eps"]) < 2e-2, rms_rel_err(out["all_eps"], emu["all_eps"])
 
 
+def test_compressor_forward_fp32_mode_vs_reference_golden(dev):
+    """Compressor.precision = "fp32": bottom_up + top_down with 3xTF32 contractions and fp32 LayerNorm / attention / GELU
+    (incl. the 32-token-over-2048-point posterior attention in fp32) against the reference's own run -- the tight bars the
+    bf16 path cannot carry (its `kls` bar is 10 %)."""
+    cfg = ns(airplane_config()).compressor
+    g = golden("encoder.npz")
+    comp, sd = build_compressor(cfg, 13, dev, gain=0.6)
+    comp.precision = "fp32"
+    torch.manual_seed(6)
+    out = comp(g["pts"].to(dev))
+    mu = torch.stack([p[1] for p in out["posteriors"][1:]])
+    rows = [("mu", rms_rel_err(mu, g["mu"])), ("all_eps", rms_rel_err(out["all_eps"], g["all_eps"])),
+            ("set", rms_rel_err(out["set"], g["set"])), ("kls", rms_rel_err(torch.stack(out["kls"]), g["kls"])),
+            ("max", abs(float(out["max"]) - float(g["max"])) / abs(float(g["max"])))]
+    print()
+    for name, r in rows:
+        print(f"Compressor.forward fp32 mode: {name:8s} rms {r:.3e} vs the reference")
+    for name, r in rows:
+        assert r < 5e-5, (name, r)   # measured 1.0e-6 ... 5.8e-6 (profiles/r02_fp32_parity.txt); the bf16 path: 1e-2 class
+    # the CPU generator ends where the reference leaves it, as in the bf16 path
+    torch.manual_seed(6)
+    O.sample_mask(2, 2048, cfg.max_outputs)
+    for _ in range(cfg.n_layers):
+        torch.randn((2, cfg.z_dim, cfg.z_scales))
+    want_state = torch.get_rng_state()
+    torch.manual_seed(6)
+    comp(g["pts"].to(dev))
+    assert torch.equal(torch.get_rng_state(), want_state)
+
+
 @pytest.mark.parametrize("pre_group,norm", [(False, "anchor"), (True, "center")])
 def test_encoder_prologue_on_own_kernels_vs_fp32_torch_expression(dev, pre_group, norm):
     """Network.py:189-199 (input Conv1d, LocalGrouper + PreExtraction with eval-mode BatchNorm, MiniPointnet, ActNorm) on the
@@ -1030,6 +1060,11 @@ def test_attention_longkv_vs_float64(dev, B, H, Nq, Nk, dh):
     ref = (w @ vd).reshape(B * Nq, H * dh)          # [B,H,Nq,dh] contiguous, re-read token-major (layers.py:197)
     assert_close = (o.double().cpu() - ref.cpu()).abs().max()
     assert float(assert_close) < 2e-2, float(assert_close)
+    # the same kernel on fp32 data (fp32 parity mode of Compressor.forward): fp32-grade
+    qf, kvf = q.float(), kv.float()
+    of = torch.empty((B * Nq, H * dh), dtype=torch.float32, device=dev)
+    ops.attention_longkv_f32(B, H, Nq, Nk, dh, qf, H * dh, kvf, torch.narrow(kvf, 1, H * dh, H * dh), 2 * H * dh, of)
+    assert float((of.double().cpu() - ref.cpu()).abs().max()) < 2e-5
 
 
 # ------------------------------------------------------------------------------------------------
