@@ -701,10 +701,21 @@ def test_condition_net_and_conditional_score_vs_reference_golden(dev):
             out_pts = model(g["x"].to(dev), g["t"].to(dev), condition={"pts": g["pts"]})
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    e_pts, e_img = rms_rel_err(pts_cond, g["pts_cond"]), rms_rel_err(img_cond, g["img_cond"])
+    print(f"\nConditionNet on own kernels (3xTF32): pts_cond rms {e_pts:.3e}  img_cond rms {e_img:.3e} vs the reference")
     assert rel_rms_err(pts_cond, g["pts_cond"]) < 1e-3, rel_rms_err(pts_cond, g["pts_cond"])
     assert rel_rms_err(img_cond, g["img_cond"]) < 1e-3, rel_rms_err(img_cond, g["img_cond"])
+    assert e_pts < 2e-5 and e_img < 2e-5, (e_pts, e_img)   # measured 2.2e-6 / 1.6e-6
     check_vs_fp32(out, g["params"])
     check_vs_fp32(out_pts, g["params_pts_only"])
+    # the whole conditional forward (prologue + cross-attention + per-sample AdaLN) in the fp32 parity mode
+    model.precision = "fp32"
+    with torch.no_grad():
+        out32 = model(g["x"].to(dev), g["t"].to(dev), condition=cond)
+    e32 = rms_rel_err(out32, g["params"])
+    print(f"conditional forward from the raw {{'img','pts'}} dict, fp32 mode: rms {e32:.3e} vs the reference "
+          f"(bf16 mode {rms_rel_err(out, g['params']):.3e})")
+    assert e32 < 5e-5, e32   # measured 5.0e-6
 
 
 @pytest.mark.parametrize("mode", ["img+pts", "pts", "img", "label"])
