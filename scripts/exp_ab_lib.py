@@ -15,7 +15,8 @@ from scripts.exp_gemm_limits import graph_of, timed_with_clocks  # noqa: E402
 
 dev = torch.device("cuda:0")
 M = int(os.environ.get("LDT_AB_M", "8192"))
-SH = {"qkv": (3072, 1024, 1), "fc_o": (1024, 1024, 3), "fc1": (4096, 1024, 2), "fc2": (1024, 4096, 3)}
+SH = {"qkv": (3072, 1024, 1), "fc_o": (1024, 1024, 3), "fc1": (4096, 1024, 2), "fc2": (1024, 4096, 3),
+      "fc1_nogelu": (4096, 1024, 1), "fc2_noresid": (1024, 4096, 0), "fc_o_noresid": (1024, 1024, 0)}   # epilogue cost probes
 
 
 def load_variant(tag):
@@ -59,7 +60,7 @@ def main():
         W = [(torch.randn((N, K), generator=g) / K ** 0.5).to(dev).bfloat16() for _ in range(24)]
         bias = torch.randn((N,), generator=g).to(dev)
         gate = torch.randn((1, N), generator=g).to(dev)
-        out = torch.zeros((M, N), dtype=torch.float32 if epi == 3 else torch.bfloat16, device=dev)
+        out = torch.zeros((M, N), dtype=torch.float32 if epi in (0, 3) else torch.bfloat16, device=dev)
         kw = dict(resid=out, gate=gate, gate_stride=0, rows_per_gate=32) if epi == 3 else {}
         graphs = {}
         for k, lib in libs.items():
