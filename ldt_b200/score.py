@@ -224,8 +224,6 @@ class Score(nn.Module):
         key = (split,) + self._fingerprint()
         if getattr(self, "_packed32", None) is not None and key == self._packed32_key:
             return self._packed32
-        if self.unet:
-            raise NotImplementedError("ldt_b200.Score: precision='tf32' / 'fp32' cover the plain (non-UNet) score net")
 
         def rw(w):   # [out, in, 1] or [out, in] parameter -> f32 [out, pad32(in)] rounded, or [out, 3*pad32(in)] split
             w2 = w.detach().reshape(w.shape[0], -1).float().contiguous()
@@ -236,20 +234,30 @@ class Score(nn.Module):
         def fb(b):
             return b.detach().float().contiguous()
 
-        Q = {"blocks": []}
+        Q = {"blocks": [], "down": []}
+
+        def pack_block(blk):
+            wq = torch.cat([blk.fc_q.weight.detach().reshape(self.hidden_size, -1),
+                            blk.fc_kv.weight.detach().reshape(2 * self.hidden_size, -1)], dim=0)
+            return {"w_qkv": rw(wq), "b_qkv": torch.cat([blk.fc_q.bias.detach(), blk.fc_kv.bias.detach()]).float().contiguous(),
+                    "w_o": rw(blk.fc_o.weight), "b_o": fb(blk.fc_o.bias),
+                    "w_fc1": rw(blk.mlp.fc[0][0].weight), "b_fc1": fb(blk.mlp.fc[0][0].bias),
+                    "w_fc2": rw(blk.mlp.out.weight), "b_fc2": fb(blk.mlp.out.bias)}
+
         with torch.no_grad():
             Q["w_in"], Q["b_in"] = rw(self.ln_in.weight), fb(self.ln_in.bias)
             ada_w, ada_b = [], []
-            for blk in self.Transformer:
-                wq = torch.cat([blk.fc_q.weight.detach().reshape(self.hidden_size, -1),
-                                blk.fc_kv.weight.detach().reshape(2 * self.hidden_size, -1)], dim=0)
-                Q["blocks"].append({
-                    "w_qkv": rw(wq), "b_qkv": torch.cat([blk.fc_q.bias.detach(), blk.fc_kv.bias.detach()]).float().contiguous(),
-                    "w_o": rw(blk.fc_o.weight), "b_o": fb(blk.fc_o.bias),
-                    "w_fc1": rw(blk.mlp.fc[0][0].weight), "b_fc1": fb(blk.mlp.fc[0][0].bias),
-                    "w_fc2": rw(blk.mlp.out.weight), "b_fc2": fb(blk.mlp.out.bias)})
+            plain = list(self.Transformer_Up) + [self.Transformer_Mid] if self.unet else list(self.Transformer)
+            for blk in plain:
+                Q["blocks"].append(pack_block(blk))
                 ada_w.append(blk.adaLN[1].weight.detach())
                 ada_b.append(blk.adaLN[1].bias.detach())
+            for blk in (self.Transformer_Down if self.unet else []):      # concat-input blocks with a Conv1d shortcut
+                d = pack_block(blk)
+                d["w_sc"], d["b_sc"] = rw(blk.shortcut.weight), fb(blk.shortcut.bias)
+                Q["down"].append(d)
+                ada_w += [blk.adaLN1[1].weight.detach(), blk.adaLN2[1].weight.detach()]
+                ada_b += [blk.adaLN1[1].bias.detach(), blk.adaLN2[1].bias.detach()]
             ada_w.append(self.ln_out.adaLN[1].weight.detach())
             ada_b.append(self.ln_out.adaLN[1].bias.detach())
             Q["w_ada"], Q["b_ada"] = rw(torch.cat(ada_w, dim=0)), torch.cat(ada_b).float().contiguous()
@@ -313,6 +321,10 @@ class Score(nn.Module):
             kv = torch.empty((M, 2 * Hd), dtype=torch.float32, device=h.device)
         k = _PtrView(qkv.data_ptr() + 4 * Hd)
         v = _PtrView(qkv.data_ptr() + 8 * Hd)
+        n_up = self.num_blocks // 2 if self.unet else 0
+        skips = []
+        if self.unet and kvc is not None:
+            raise NotImplementedError("unet score net with condition tokens (see _run_tokens_unet)")
         for i, W in enumerate(Q["blocks"]):
             base = i * 6 * Hd
             ops.layernorm_mod_f32(h, a, shift=mview(base), scale=mview(base + Hd), mod_stride=mod_stride, rows_per_mod=T,
@@ -331,7 +343,28 @@ class Score(nn.Module):
             gemm(a, a3, W["w_fc1"], W["b_fc1"], hid, EPI_BIAS_GELU_F32)
             gemm(hid, hid3, W["w_fc2"], W["b_fc2"], h, EPI_GATE_RESID_F32, resid=h, gate=mview(base + 5 * Hd),
                  gate_stride=mod_stride, rows_per_gate=T)
-        base = self.num_blocks * 6 * Hd
+            if i < n_up:
+                skips.append(h.clone())                                   # x_list.append(x)  (score.py:141)
+        base = len(Q["blocks"]) * 6 * Hd
+        for j, W in enumerate(Q["down"]):
+            # x = cat(x, x_list.pop()) on channels (:145); adaLN1 -> (shift, scale) [2H each], adaLN2 -> (gate_msa, shift_mlp,
+            # scale_mlp, gate_mlp) [H each] (layers.py:216-217); the attention output is added to shortcut(x) (:173-175)
+            hcat = torch.cat([h, skips[n_up - 1 - j]], dim=1)
+            acat = torch.empty_like(hcat)
+            ops.layernorm_mod_f32(hcat, acat, shift=mview(base), scale=mview(base + 2 * Hd), mod_stride=mod_stride, rows_per_mod=T,
+                                  round_tf32=rnd)
+            gemm(acat, None, W["w_qkv"], W["b_qkv"], qkv, EPI_BIAS_F32)
+            ops.attention_nk32_f32(B, heads, T, dh, qkv, 3 * Hd, k, v, 3 * Hd, att, round_tf32=rnd)
+            hsc = torch.empty_like(h)
+            gemm(hcat if split else ops.round_pad_tf32(hcat), None, W["w_sc"], W["b_sc"], hsc, EPI_BIAS_F32)
+            gemm(att, a3, W["w_o"], W["b_o"], h, EPI_GATE_RESID_F32, resid=hsc, gate=mview(base + 4 * Hd),
+                 gate_stride=mod_stride, rows_per_gate=T)
+            ops.layernorm_mod_f32(h, a, shift=mview(base + 5 * Hd), scale=mview(base + 6 * Hd), mod_stride=mod_stride,
+                                  rows_per_mod=T, round_tf32=rnd)
+            gemm(a, a3, W["w_fc1"], W["b_fc1"], hid, EPI_BIAS_GELU_F32)
+            gemm(hid, hid3, W["w_fc2"], W["b_fc2"], h, EPI_GATE_RESID_F32, resid=h, gate=mview(base + 7 * Hd),
+                 gate_stride=mod_stride, rows_per_gate=T)
+            base += 8 * Hd
         ops.layernorm_mod_f32(h, a, shift=mview(base), scale=mview(base + Hd), mod_stride=mod_stride, rows_per_mod=T, round_tf32=rnd)
         gemm(a, a3, Q["w_out"], Q["b_out"], out, EPI_BIAS_F32, N=self.z_dim)
         return out

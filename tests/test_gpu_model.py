@@ -907,6 +907,18 @@ def test_score_unet_vs_reference_golden_and_fused_loop(dev):
     generic = sde.sample_discrete(lambda t, x, label=None, condition=None: tr.score_fn(t, x), 4, 8, "ancestral", None, 1,
                                   (32, 120), 1e-6, False, True, 0.01, dev)
     assert rel_rms_err(fused, generic) < 1e-5, rel_rms_err(fused, generic)
+    # the two f32-operand parity modes on the UNet wiring (concat stream, adaLN1 / adaLN2, Conv1d shortcut)
+    print()
+    for mode, tol in (("tf32", 3e-3), ("fp32", 5e-5)):
+        model.precision = mode
+        with torch.no_grad():
+            o = model(g["x"].to(dev), g["t"].to(dev))
+            oc = model(g["x"].to(dev), g["t"].to(dev), condition=(None, g["img_cond"].to(dev)))
+        r, rc = rms_rel_err(o, g["params"]), rms_rel_err(oc, g["params_cond"])
+        print(f"unet score net, {mode} mode: rms {r:.3e} (with the condition vector {rc:.3e}) vs the reference "
+              f"(bf16 mode {rms_rel_err(out, g['params']):.3e})")
+        assert r < tol and rc < tol, (mode, r, rc)
+    model.precision = "bf16"
 
 
 # ------------------------------------------------------------------------------------------------
