@@ -789,7 +789,9 @@ def test_fps_bit_exact_vs_reference_in_tree_cuda_kernel(dev, b, n, m):
     source where it lies into oracle/_ref/libref_fps.so) run on the same GPU: identical index sequences.  That kernel has
     no small-norm skip rule, which is ldt_furthest_point_sample with min_sq_norm < 0; it reads channels-first [b,3,n]
     coordinates and a distance scratch initialised to 1e38 (sampling.cpp:52-53).  n = 4000 crosses its 3072-point shared
-    buffer.  Exact distance ties (duplicate points) are the one documented difference and do not occur in these clouds."""
+    buffer.  Exact distance ties (duplicate points) are the one documented difference and do not occur in these clouds.
+    (compute-sanitizer racecheck flags a write-after-read race on dists_i[0] inside the reference's kernel; it does not show at
+    these sizes -- the comparison has been bit-identical on every run -- but a mismatch here should first be re-run.)"""
     path = os.path.join(ROOT, "oracle", "_ref", "libref_fps.so")
     assert os.path.exists(path), "oracle/_ref/libref_fps.so missing: run `make -C oracle` in the build container"
     R = C.CDLL(path)
